@@ -1,0 +1,1072 @@
+// Host side of the C ABI declared in include/ekf_slam_b200.h: handle management, staging, kernel
+// launches.  No algorithmic work happens on the host — there is deliberately no CPU fallback.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "../../include/ekf_slam_b200.h"
+#include "ekf_fused.cuh"
+#include "ekf_large.cuh"
+
+using namespace ekf;
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CU(expr)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e_ = (expr);                                                                         \
+        if (e_ != cudaSuccess) {                                                                         \
+            cudaGetLastError();                                                                          \
+            return fail((int)e_, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
+        }                                                                                                \
+    } while (0)
+
+constexpr int kFusedMaxN = 64;  // landmarks; Sigma (131^2 fp64 = 137 KB) must fit shared memory
+constexpr int kRing = 8;
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) {
+        cudaGetDevice(&prev);
+        if (prev != dev) cudaSetDevice(dev);
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+int max_smem_optin(int device) {
+    int v = 0;
+    cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+    return v;
+}
+
+// Launch the fused one-warp-per-filter kernel (n = 20 gets the fully unrolled instantiation).
+int launch_fused(const FusedParams& p, cudaStream_t stream, int device) {
+    const FusedSmem L(p.n, p.m_max);
+    if (L.total > max_smem_optin(device))
+        return fail(EKF_ERR_UNSUPPORTED, "fused engine: %d B of shared memory needed for n=%d", L.total, p.n);
+    if (p.B <= 0) return EKF_OK;
+    if (p.B > 0x7fffffffLL) return fail(EKF_ERR_INVALID, "batch too large for one launch");
+    static int set20[64] = {0}, set0[64] = {0};
+    if (p.n == 20) {
+        if (set20[device] < L.total) {
+            CU(cudaFuncSetAttribute(ekf_fused_kernel<20>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
+            set20[device] = L.total;
+        }
+        ekf_fused_kernel<20><<<(unsigned)p.B, 32, L.total, stream>>>(p);
+    } else {
+        if (set0[device] < L.total) {
+            CU(cudaFuncSetAttribute(ekf_fused_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
+            set0[device] = L.total;
+        }
+        ekf_fused_kernel<0><<<(unsigned)p.B, 32, L.total, stream>>>(p);
+    }
+    CU(cudaGetLastError());
+    return EKF_OK;
+}
+
+__global__ void k_fused_init(double* sigma, double* state, int32_t* init_flag, long long B, int N, int sig_stride,
+                             int st_stride) {
+    const long long b = blockIdx.x;
+    if (b >= B) return;
+    double* s = sigma + b * (long long)sig_stride;
+    for (int e = threadIdx.x; e < sig_stride; e += blockDim.x) {
+        const int r = e / N, c = e - r * N;
+        s[e] = (e < N * N && r == c && r >= 3) ? kSigma0 : 0.0;
+    }
+    for (int e = threadIdx.x; e < st_stride; e += blockDim.x) state[b * (long long)st_stride + e] = 0.0;
+    if (threadIdx.x == 0) init_flag[b] = 0;
+}
+
+__global__ void k_maha_one(const double* sig, long long ld, const double* state, int i, double sx, double sy,
+                           double* out) {
+    double zr, zphi;
+    range_bearing(sx, sy, zr, zphi);
+    *out = maha_distance(sig, ld, i, state[3 + 2 * i], state[4 + 2 * i], zr, zphi, state[0], state[1], state[2]);
+}
+
+__global__ void k_normalize(const double* in, double* out, long long count) {
+    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < count) out[k] = normalize_angle(in[k]);
+}
+
+__global__ void k_gather_poses(const double* state, long long B, int st_stride, double* out) {
+    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= 3 * B) return;
+    const long long b = k / 3;
+    out[k] = state[b * st_stride + (k - 3 * b)];
+}
+
+// truth[b] = {x, y, theta}; state = {theta, x, y}
+__global__ void k_pose_error(const double* state, long long B, int st_stride, const double* truth, double* acc4) {
+    double ex = 0, ey = 0, et = 0;
+    for (long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x; b < B; b += (long long)gridDim.x * blockDim.x) {
+        const double* s = state + b * st_stride;
+        const double dx = s[1] - truth[3 * b], dy = s[2] - truth[3 * b + 1];
+        const double dt = normalize_angle(s[0] - truth[3 * b + 2]);
+        ex += dx * dx;
+        ey += dy * dy;
+        et += dt * dt;
+    }
+    for (int off = 16; off > 0; off >>= 1) {
+        ex += __shfl_xor_sync(0xffffffffu, ex, off);
+        ey += __shfl_xor_sync(0xffffffffu, ey, off);
+        et += __shfl_xor_sync(0xffffffffu, et, off);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(acc4 + 0, ex);
+        atomicAdd(acc4 + 1, ey);
+        atomicAdd(acc4 + 2, et);
+    }
+}
+
+}  // namespace
+
+// ======================================================================================= handles
+struct ekf_filter {
+    int n = 0, N = 0, device = 0, engine = 0;
+    cudaStream_t stream = nullptr;
+    uint64_t launches = 0;
+    // persistent filter state
+    double* d_sigma = nullptr;
+    long long ld = 0;          // row stride (stream engine: padded; fused engine: N)
+    long long sig_elems = 0;   // allocated doubles
+    double* d_state = nullptr;
+    int st_stride = 0;
+    int32_t* d_init_flag = nullptr;
+    unsigned long long* d_nupd = nullptr;
+    int init_flag_host = 0;  // mirror used by the stream engine's host-side sequencing
+    // inputs / outputs on the device
+    int m_cap = 0;
+    double* d_in = nullptr;       // xy (2n) or meas (2 m_cap)
+    uint8_t* d_flags = nullptr;   // visible (n) / known (n)
+    int32_t* d_mcount = nullptr;
+    double* d_twist = nullptr;
+    int32_t* d_assoc = nullptr;
+    double* d_dmin = nullptr;
+    double* d_second = nullptr;
+    uint8_t* d_created = nullptr;
+    double* d_scalar = nullptr;  // maha out
+    // pinned staging ring
+    unsigned char* h_ring[kRing] = {nullptr};
+    cudaEvent_t ring_ev[kRing] = {nullptr};
+    size_t ring_bytes = 0;
+    int ring_pos = 0;
+    unsigned char* h_out = nullptr;  // pinned output staging
+    size_t h_out_bytes = 0;
+    // stream engine scratch
+    double2* d_K2 = nullptr;
+    double2* d_W2 = nullptr;
+    double* d_motion = nullptr;
+    double* d_pose0 = nullptr;
+    UpdateCmd* d_cmd = nullptr;
+    Special5* d_sp = nullptr;
+    AssocPartial* d_partials = nullptr;
+    unsigned int* d_done = nullptr;
+    int* d_known_count = nullptr;
+    int assoc_blocks = 0;
+    int sm_count = 148;
+};
+
+namespace {
+
+int free_filter(ekf_filter* h) {
+    if (!h) return EKF_OK;
+    DeviceGuard g(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    cudaFree(h->d_sigma);
+    cudaFree(h->d_state);
+    cudaFree(h->d_init_flag);
+    cudaFree(h->d_nupd);
+    cudaFree(h->d_in);
+    cudaFree(h->d_flags);
+    cudaFree(h->d_mcount);
+    cudaFree(h->d_twist);
+    cudaFree(h->d_assoc);
+    cudaFree(h->d_dmin);
+    cudaFree(h->d_second);
+    cudaFree(h->d_created);
+    cudaFree(h->d_scalar);
+    cudaFree(h->d_K2);
+    cudaFree(h->d_W2);
+    cudaFree(h->d_motion);
+    cudaFree(h->d_pose0);
+    cudaFree(h->d_cmd);
+    cudaFree(h->d_sp);
+    cudaFree(h->d_partials);
+    cudaFree(h->d_done);
+    cudaFree(h->d_known_count);
+    for (int i = 0; i < kRing; ++i) {
+        if (h->h_ring[i]) cudaFreeHost(h->h_ring[i]);
+        if (h->ring_ev[i]) cudaEventDestroy(h->ring_ev[i]);
+    }
+    if (h->h_out) cudaFreeHost(h->h_out);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    cudaGetLastError();
+    delete h;
+    return EKF_OK;
+}
+
+// (re)size the measurement-count dependent buffers
+int ensure_m_cap(ekf_filter* h, int m) {
+    if (m <= h->m_cap) return EKF_OK;
+    const int cap = std::max(std::max(m, h->n), 32);
+    cudaStreamSynchronize(h->stream);
+    cudaFree(h->d_in);
+    cudaFree(h->d_assoc);
+    cudaFree(h->d_dmin);
+    cudaFree(h->d_second);
+    cudaFree(h->d_created);
+    h->d_in = nullptr;
+    h->d_assoc = nullptr;
+    h->d_dmin = h->d_second = nullptr;
+    h->d_created = nullptr;
+    CU(cudaMalloc(&h->d_in, sizeof(double) * 2 * cap));
+    CU(cudaMalloc(&h->d_assoc, sizeof(int32_t) * cap));
+    CU(cudaMalloc(&h->d_dmin, sizeof(double) * cap));
+    CU(cudaMalloc(&h->d_second, sizeof(double) * cap));
+    CU(cudaMalloc(&h->d_created, cap));
+    const size_t need = sizeof(double) * 2 * cap + h->n + 64;
+    if (need > h->ring_bytes) {
+        for (int i = 0; i < kRing; ++i) {
+            if (h->h_ring[i]) cudaFreeHost(h->h_ring[i]);
+            h->h_ring[i] = nullptr;
+            CU(cudaMallocHost((void**)&h->h_ring[i], need));
+        }
+        h->ring_bytes = need;
+    }
+    const size_t out_need = (size_t)cap * (sizeof(int32_t) + 2 * sizeof(double) + 1) + (size_t)h->n + 64 +
+                            sizeof(double) * (size_t)h->N;
+    if (out_need > h->h_out_bytes) {
+        if (h->h_out) cudaFreeHost(h->h_out);
+        h->h_out = nullptr;
+        CU(cudaMallocHost((void**)&h->h_out, out_need));
+        h->h_out_bytes = out_need;
+    }
+    h->m_cap = cap;
+    return EKF_OK;
+}
+
+// next pinned staging slot, safe to overwrite
+int ring_acquire(ekf_filter* h, unsigned char** slot, cudaEvent_t* ev) {
+    const int i = h->ring_pos;
+    h->ring_pos = (i + 1) % kRing;
+    CU(cudaEventSynchronize(h->ring_ev[i]));
+    *slot = h->h_ring[i];
+    *ev = h->ring_ev[i];
+    return EKF_OK;
+}
+
+FusedParams fused_params(ekf_filter* h, int mode, int m_max) {
+    FusedParams p;
+    memset(&p, 0, sizeof(p));
+    p.sigma = h->d_sigma;
+    p.state = h->d_state;
+    p.init_flag = h->d_init_flag;
+    p.known = h->d_flags;
+    p.twists = h->d_twist;
+    p.xy = h->d_in;
+    p.vis = h->d_flags;
+    p.mcount = h->d_mcount;
+    p.assoc_out = h->d_assoc;
+    p.dmin_out = h->d_dmin;
+    p.second_out = h->d_second;
+    p.created_out = h->d_created;
+    p.n_updates = h->d_nupd;
+    p.B = 1;
+    p.n = h->n;
+    p.m_max = m_max;
+    p.mode = mode;
+    p.sig_stride = (int)h->sig_elems;
+    p.st_stride = h->st_stride;
+    return p;
+}
+
+int sweep_grid(const ekf_filter* h) {
+    const long long chunks = (h->ld + kSweepChunk - 1) / kSweepChunk;
+    const long long row_blocks = (h->N + kSweepRows - 1) / kSweepRows;
+    const long long tiles = chunks * row_blocks;
+    const long long cap = (long long)h->sm_count * 8;
+    return (int)std::max(1LL, std::min(tiles, cap));
+}
+
+// one landmark correction on the stream engine: gain then sweep
+int stream_correct(ekf_filter* h, const double* pose_src, const UpdateCmd* cmd, int lm, double sx, double sy) {
+    const int gb = (int)((h->ld + 255) / 256);
+    k_large_gain<<<gb, 256, 0, h->stream>>>(h->d_sigma, h->ld, h->N, h->d_state, pose_src, cmd, lm, sx, sy, h->d_K2,
+                                            h->d_W2, h->d_sp);
+    k_large_sweep<<<sweep_grid(h), kSweepThreads, 0, h->stream>>>(h->d_sigma, h->ld, h->N, h->d_K2, h->d_W2, cmd,
+                                                                  h->d_sp, h->d_state, h->d_nupd);
+    h->launches += 2;
+    CU(cudaGetLastError());
+    return EKF_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* ekf_version(void) { return "ekf-slam-ml_b200 0.1 (sm_100a)"; }
+const char* ekf_last_error(void) { return g_err; }
+
+int ekf_device_count(int* count_out) {
+    if (!count_out) return fail(EKF_ERR_INVALID, "null argument");
+    int c = 0;
+    cudaError_t e = cudaGetDeviceCount(&c);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        *count_out = 0;
+        return fail((int)e, "cudaGetDeviceCount: %s", cudaGetErrorString(e));
+    }
+    *count_out = c;
+    return EKF_OK;
+}
+
+int ekf_host_alloc(void** out, uint64_t bytes) {
+    if (!out) return fail(EKF_ERR_INVALID, "null argument");
+    CU(cudaMallocHost(out, bytes ? bytes : 1));
+    return EKF_OK;
+}
+int ekf_host_free(void* p) {
+    if (p) CU(cudaFreeHost(p));
+    return EKF_OK;
+}
+
+int ekf_create_ex(int n, int device, int engine, ekf_filter** out) {
+    if (!out) return fail(EKF_ERR_INVALID, "null out pointer");
+    *out = nullptr;
+    if (n <= 0 || n > 500000) return fail(EKF_ERR_INVALID, "n_landmarks=%d out of range", n);
+    int count = 0;
+    int rc = ekf_device_count(&count);
+    if (rc) return rc;
+    if (device < 0 || device >= count) return fail(EKF_ERR_INVALID, "device %d not available (%d visible)", device, count);
+    if (engine == EKF_ENGINE_AUTO) engine = (n <= kFusedMaxN) ? EKF_ENGINE_FUSED : EKF_ENGINE_STREAM;
+    if (engine != EKF_ENGINE_FUSED && engine != EKF_ENGINE_STREAM) return fail(EKF_ERR_INVALID, "unknown engine %d", engine);
+    if (engine == EKF_ENGINE_FUSED && n > kFusedMaxN)
+        return fail(EKF_ERR_UNSUPPORTED, "fused engine supports n <= %d", kFusedMaxN);
+    DeviceGuard g(device);
+    ekf_filter* h = new (std::nothrow) ekf_filter();
+    if (!h) return fail(EKF_ERR_STATE, "out of host memory");
+    h->n = n;
+    h->N = 3 + 2 * n;
+    h->device = device;
+    h->engine = engine;
+    cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device);
+#define CUH(expr)                          \
+    do {                                   \
+        cudaError_t e_ = (expr);           \
+        if (e_ != cudaSuccess) {           \
+            cudaGetLastError();            \
+            int code_ = fail((int)e_, "%s failed: %s", #expr, cudaGetErrorString(e_)); \
+            free_filter(h);                \
+            return code_;                  \
+        }                                  \
+    } while (0)
+    CUH(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    for (int i = 0; i < kRing; ++i) CUH(cudaEventCreateWithFlags(&h->ring_ev[i], cudaEventDisableTiming));
+    h->st_stride = fused_round16(h->N);
+    if (engine == EKF_ENGINE_FUSED) {
+        h->ld = h->N;
+        h->sig_elems = fused_round16(h->N * h->N);
+    } else {
+        h->ld = fused_round16(h->N);
+        h->sig_elems = (long long)h->N * h->ld;
+    }
+    CUH(cudaMalloc(&h->d_sigma, sizeof(double) * (size_t)h->sig_elems));
+    CUH(cudaMalloc(&h->d_state, sizeof(double) * h->st_stride));
+    CUH(cudaMalloc(&h->d_init_flag, sizeof(int32_t)));
+    CUH(cudaMalloc(&h->d_nupd, sizeof(unsigned long long)));
+    CUH(cudaMalloc(&h->d_flags, (size_t)n + 16));
+    CUH(cudaMalloc(&h->d_mcount, sizeof(int32_t)));
+    CUH(cudaMalloc(&h->d_twist, 2 * sizeof(double)));
+    CUH(cudaMalloc(&h->d_scalar, sizeof(double)));
+    CUH(cudaMemsetAsync(h->d_nupd, 0, sizeof(unsigned long long), h->stream));
+    if (engine == EKF_ENGINE_FUSED) {
+        k_fused_init<<<1, 256, 0, h->stream>>>(h->d_sigma, h->d_state, h->d_init_flag, 1, h->N, (int)h->sig_elems,
+                                                h->st_stride);
+    } else {
+        CUH(cudaMemsetAsync(h->d_sigma, 0, sizeof(double) * (size_t)h->sig_elems, h->stream));
+        CUH(cudaMemsetAsync(h->d_state, 0, sizeof(double) * h->st_stride, h->stream));
+        CUH(cudaMemsetAsync(h->d_init_flag, 0, sizeof(int32_t), h->stream));
+        k_large_init_sigma<<<(h->N + 255) / 256, 256, 0, h->stream>>>(h->d_sigma, h->ld, h->N);
+        CUH(cudaMalloc(&h->d_K2, sizeof(double2) * (size_t)h->ld));
+        CUH(cudaMalloc(&h->d_W2, sizeof(double2) * (size_t)h->ld));
+        CUH(cudaMalloc(&h->d_motion, 2 * sizeof(double)));
+        CUH(cudaMalloc(&h->d_pose0, 3 * sizeof(double)));
+        CUH(cudaMalloc(&h->d_cmd, sizeof(UpdateCmd)));
+        CUH(cudaMalloc(&h->d_sp, sizeof(Special5)));
+        h->assoc_blocks = std::max(1, std::min((n + 255) / 256, 1024));
+        CUH(cudaMalloc(&h->d_partials, sizeof(AssocPartial) * h->assoc_blocks));
+        CUH(cudaMalloc(&h->d_done, sizeof(unsigned int)));
+        CUH(cudaMalloc(&h->d_known_count, sizeof(int)));
+        CUH(cudaMemsetAsync(h->d_done, 0, sizeof(unsigned int), h->stream));
+        CUH(cudaMemsetAsync(h->d_sp, 0, sizeof(Special5), h->stream));
+        CUH(cudaMemsetAsync(h->d_cmd, 0, sizeof(UpdateCmd), h->stream));
+        CUH(cudaMemsetAsync(h->d_K2, 0, sizeof(double2) * (size_t)h->ld, h->stream));
+        CUH(cudaMemsetAsync(h->d_W2, 0, sizeof(double2) * (size_t)h->ld, h->stream));
+    }
+    h->launches += 1;
+    CUH(cudaGetLastError());
+    rc = ensure_m_cap(h, std::max(n, 32));
+    if (rc) {
+        free_filter(h);
+        return rc;
+    }
+    CUH(cudaStreamSynchronize(h->stream));
+#undef CUH
+    *out = h;
+    return EKF_OK;
+}
+
+int ekf_create(int n, int device, ekf_filter** out) { return ekf_create_ex(n, device, EKF_ENGINE_AUTO, out); }
+
+int ekf_clone(ekf_filter* src, ekf_filter** out) {
+    if (!src || !out) return fail(EKF_ERR_INVALID, "null argument");
+    int rc = ekf_create_ex(src->n, src->device, src->engine, out);
+    if (rc) return rc;
+    ekf_filter* h = *out;
+    DeviceGuard g(src->device);
+    CU(cudaStreamSynchronize(src->stream));
+    CU(cudaMemcpy(h->d_sigma, src->d_sigma, sizeof(double) * (size_t)src->sig_elems, cudaMemcpyDeviceToDevice));
+    CU(cudaMemcpy(h->d_state, src->d_state, sizeof(double) * src->st_stride, cudaMemcpyDeviceToDevice));
+    CU(cudaMemcpy(h->d_init_flag, src->d_init_flag, sizeof(int32_t), cudaMemcpyDeviceToDevice));
+    CU(cudaMemcpy(h->d_nupd, src->d_nupd, sizeof(unsigned long long), cudaMemcpyDeviceToDevice));
+    h->init_flag_host = src->init_flag_host;
+    return EKF_OK;
+}
+
+int ekf_destroy(ekf_filter* h) { return free_filter(h); }
+int ekf_num_landmarks(const ekf_filter* h) { return h ? h->n : EKF_ERR_INVALID; }
+int ekf_engine(const ekf_filter* h) { return h ? h->engine : EKF_ERR_INVALID; }
+void* ekf_stream(ekf_filter* h) { return h ? (void*)h->stream : nullptr; }
+
+int ekf_predict(ekf_filter* h, double dtheta, double dx) {
+    if (!h) return fail(EKF_ERR_INVALID, "null handle");
+    DeviceGuard g(h->device);
+    if (h->engine == EKF_ENGINE_FUSED) {
+        unsigned char* slot;
+        cudaEvent_t ev;
+        int rc = ring_acquire(h, &slot, &ev);
+        if (rc) return rc;
+        double* tw = reinterpret_cast<double*>(slot);
+        tw[0] = dtheta;
+        tw[1] = dx;
+        CU(cudaMemcpyAsync(h->d_twist, tw, 2 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        CU(cudaEventRecord(ev, h->stream));
+        FusedParams p = fused_params(h, kDoPredict, 1);
+        rc = launch_fused(p, h->stream, h->device);
+        h->launches += 1;
+        return rc;
+    }
+    k_large_motion<<<1, 32, 0, h->stream>>>(h->d_state, h->d_sigma, h->ld, dtheta, dx, h->d_motion);
+    k_large_predict_strips<<<(h->N - 3 + 255) / 256, 256, 0, h->stream>>>(h->d_sigma, h->ld, h->N, h->d_motion);
+    h->launches += 2;
+    CU(cudaGetLastError());
+    return EKF_OK;
+}
+
+int ekf_measurement(ekf_filter* h, const double* xy, const uint8_t* visible) {
+    if (!h || !xy || !visible) return fail(EKF_ERR_INVALID, "null argument");
+    DeviceGuard g(h->device);
+    const int n = h->n;
+    if (h->engine == EKF_ENGINE_FUSED) {
+        unsigned char* slot;
+        cudaEvent_t ev;
+        int rc = ring_acquire(h, &slot, &ev);
+        if (rc) return rc;
+        memcpy(slot, xy, sizeof(double) * 2 * n);
+        memcpy(slot + sizeof(double) * 2 * n, visible, n);
+        CU(cudaMemcpyAsync(h->d_in, slot, sizeof(double) * 2 * n, cudaMemcpyHostToDevice, h->stream));
+        CU(cudaMemcpyAsync(h->d_flags, slot + sizeof(double) * 2 * n, n, cudaMemcpyHostToDevice, h->stream));
+        CU(cudaEventRecord(ev, h->stream));
+        FusedParams p = fused_params(h, kDoMeasurement, 1);
+        rc = launch_fused(p, h->stream, h->device);
+        h->launches += 1;
+        return rc;
+    }
+    // stream engine: the host sequences one (gain, sweep) pair per visible landmark; readings travel as kernel
+    // arguments, the entry-time pose is snapshotted on the device (ekf_slam.cpp:109-111).
+    if (!h->init_flag_host) {
+        unsigned char* slot;
+        cudaEvent_t ev;
+        int rc = ring_acquire(h, &slot, &ev);
+        if (rc) return rc;
+        memcpy(slot, xy, sizeof(double) * 2 * n);
+        CU(cudaMemcpyAsync(h->d_in, slot, sizeof(double) * 2 * n, cudaMemcpyHostToDevice, h->stream));
+        CU(cudaEventRecord(ev, h->stream));
+        k_large_init_landmarks<<<(n + 255) / 256, 256, 0, h->stream>>>(h->d_state, h->d_in, n, h->d_init_flag);
+        h->launches += 1;
+        h->init_flag_host = 1;
+    }
+    CU(cudaMemcpyAsync(h->d_pose0, h->d_state, 3 * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    for (int i = 0; i < n; ++i) {
+        if (!visible[i]) continue;
+        int rc = stream_correct(h, h->d_pose0, nullptr, i, xy[2 * i], xy[2 * i + 1]);
+        if (rc) return rc;
+    }
+    return EKF_OK;
+}
+
+int ekf_data_association(ekf_filter* h, const double* xy, int m, uint8_t* known, int32_t* assoc_out,
+                         double* dmin_out, double* second_out, uint8_t* created_out) {
+    if (!h || !known || m < 0 || (m > 0 && !xy)) return fail(EKF_ERR_INVALID, "invalid argument");
+    DeviceGuard g(h->device);
+    const int n = h->n;
+    if (m == 0) return EKF_OK;
+    int rc = ensure_m_cap(h, m);
+    if (rc) return rc;
+    unsigned char* slot;
+    cudaEvent_t ev;
+    rc = ring_acquire(h, &slot, &ev);
+    if (rc) return rc;
+    memcpy(slot, xy, sizeof(double) * 2 * m);
+    memcpy(slot + sizeof(double) * 2 * m, known, n);
+    int32_t* slot_i = reinterpret_cast<int32_t*>(slot + sizeof(double) * 2 * m + ((n + 15) & ~15));
+    int known_count = 0;
+    while (known_count < n && known[known_count]) ++known_count;  // leading-true prefix, ekf_slam.cpp:281-288
+    slot_i[0] = m;
+    slot_i[1] = known_count;
+    CU(cudaMemcpyAsync(h->d_in, slot, sizeof(double) * 2 * m, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(h->d_flags, slot + sizeof(double) * 2 * m, n, cudaMemcpyHostToDevice, h->stream));
+    if (h->engine == EKF_ENGINE_FUSED) {
+        CU(cudaMemcpyAsync(h->d_mcount, slot_i, sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+        CU(cudaEventRecord(ev, h->stream));
+        FusedParams p = fused_params(h, kDoAssociation, m);
+        rc = launch_fused(p, h->stream, h->device);
+        h->launches += 1;
+        if (rc) return rc;
+    } else {
+        CU(cudaMemcpyAsync(h->d_known_count, slot_i + 1, sizeof(int), cudaMemcpyHostToDevice, h->stream));
+        CU(cudaEventRecord(ev, h->stream));
+        for (int j = 0; j < m; ++j) {
+            k_large_assoc<<<h->assoc_blocks, 256, 0, h->stream>>>(h->d_sigma, h->ld, h->d_state, n, h->d_in, j,
+                                                                   h->d_known_count, h->d_partials, h->d_done, h->d_cmd,
+                                                                   h->d_assoc, h->d_dmin, h->d_second, h->d_created);
+            h->launches += 1;
+            rc = stream_correct(h, h->d_state, h->d_cmd, 0, 0.0, 0.0);
+            if (rc) return rc;
+        }
+    }
+    // outputs: one pinned staging area, one synchronisation
+    unsigned char* o = h->h_out;
+    int32_t* o_assoc = reinterpret_cast<int32_t*>(o);
+    double* o_dmin = reinterpret_cast<double*>(o + (((size_t)m * 4 + 15) & ~(size_t)15));
+    double* o_second = o_dmin + m;
+    uint8_t* o_created = reinterpret_cast<uint8_t*>(o_second + m);
+    uint8_t* o_known = o_created + ((m + 15) & ~15);
+    int* o_kc = reinterpret_cast<int*>(o_known + ((n + 15) & ~15));
+    CU(cudaMemcpyAsync(o_assoc, h->d_assoc, sizeof(int32_t) * m, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaMemcpyAsync(o_dmin, h->d_dmin, sizeof(double) * m, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaMemcpyAsync(o_second, h->d_second, sizeof(double) * m, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaMemcpyAsync(o_created, h->d_created, m, cudaMemcpyDeviceToHost, h->stream));
+    if (h->engine == EKF_ENGINE_FUSED)
+        CU(cudaMemcpyAsync(o_known, h->d_flags, n, cudaMemcpyDeviceToHost, h->stream));
+    else
+        CU(cudaMemcpyAsync(o_kc, h->d_known_count, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    if (assoc_out) memcpy(assoc_out, o_assoc, sizeof(int32_t) * m);
+    if (dmin_out) memcpy(dmin_out, o_dmin, sizeof(double) * m);
+    if (second_out) memcpy(second_out, o_second, sizeof(double) * m);
+    if (created_out) memcpy(created_out, o_created, m);
+    if (h->engine == EKF_ENGINE_FUSED) {
+        memcpy(known, o_known, n);
+    } else {
+        for (int i = known_count; i < *o_kc && i < n; ++i) known[i] = 1;
+    }
+    return EKF_OK;
+}
+
+int ekf_maha(ekf_filter* h, double mx, double my, int landmark, double* d_out) {
+    if (!h || !d_out || landmark < 0 || landmark >= h->n) return fail(EKF_ERR_INVALID, "invalid argument");
+    DeviceGuard g(h->device);
+    k_maha_one<<<1, 1, 0, h->stream>>>(h->d_sigma, h->ld, h->d_state, landmark, mx, my, h->d_scalar);
+    h->launches += 1;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(d_out, h->d_scalar, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return EKF_OK;
+}
+
+int ekf_get_state(ekf_filter* h, double* out) {
+    if (!h || !out) return fail(EKF_ERR_INVALID, "null argument");
+    DeviceGuard g(h->device);
+    CU(cudaMemcpyAsync(out, h->d_state, sizeof(double) * h->N, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return EKF_OK;
+}
+int ekf_set_state(ekf_filter* h, const double* in) {
+    if (!h || !in) return fail(EKF_ERR_INVALID, "null argument");
+    DeviceGuard g(h->device);
+    CU(cudaMemcpyAsync(h->d_state, in, sizeof(double) * h->N, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return EKF_OK;
+}
+int ekf_get_pose(ekf_filter* h, double* out3) {
+    if (!h || !out3) return fail(EKF_ERR_INVALID, "null argument");
+    DeviceGuard g(h->device);
+    CU(cudaMemcpyAsync(out3, h->d_state, 3 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return EKF_OK;
+}
+int ekf_get_landmarks(ekf_filter* h, double* out) {
+    if (!h || !out) return fail(EKF_ERR_INVALID, "null argument");
+    DeviceGuard g(h->device);
+    CU(cudaMemcpyAsync(out, h->d_state + 3, sizeof(double) * 2 * h->n, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return EKF_OK;
+}
+int ekf_get_sigma(ekf_filter* h, double* out, int64_t ld) {
+    if (!h || !out || ld < h->N) return fail(EKF_ERR_INVALID, "invalid argument");
+    DeviceGuard g(h->device);
+    CU(cudaMemcpy2DAsync(out, sizeof(double) * ld, h->d_sigma, sizeof(double) * h->ld, sizeof(double) * h->N, h->N,
+                         cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return EKF_OK;
+}
+int ekf_set_sigma(ekf_filter* h, const double* in, int64_t ld) {
+    if (!h || !in || ld < h->N) return fail(EKF_ERR_INVALID, "invalid argument");
+    DeviceGuard g(h->device);
+    CU(cudaMemcpy2DAsync(h->d_sigma, sizeof(double) * h->ld, in, sizeof(double) * ld, sizeof(double) * h->N, h->N,
+                         cudaMemcpyHostToDevice, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return EKF_OK;
+}
+int ekf_get_init_flag(ekf_filter* h, int* out) {
+    if (!h || !out) return fail(EKF_ERR_INVALID, "null argument");
+    DeviceGuard g(h->device);
+    int32_t v = 0;
+    CU(cudaMemcpyAsync(&v, h->d_init_flag, sizeof(v), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    *out = v;
+    return EKF_OK;
+}
+int ekf_set_init_flag(ekf_filter* h, int v) {
+    if (!h) return fail(EKF_ERR_INVALID, "null handle");
+    DeviceGuard g(h->device);
+    const int32_t f = v ? 1 : 0;
+    CU(cudaMemcpyAsync(h->d_init_flag, &f, sizeof(f), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    h->init_flag_host = f;
+    return EKF_OK;
+}
+int ekf_update_count(ekf_filter* h, uint64_t* out) {
+    if (!h || !out) return fail(EKF_ERR_INVALID, "null argument");
+    DeviceGuard g(h->device);
+    unsigned long long v = 0;
+    CU(cudaMemcpyAsync(&v, h->d_nupd, sizeof(v), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    *out = v;
+    return EKF_OK;
+}
+int ekf_sync(ekf_filter* h) {
+    if (!h) return fail(EKF_ERR_INVALID, "null handle");
+    DeviceGuard g(h->device);
+    CU(cudaStreamSynchronize(h->stream));
+    return EKF_OK;
+}
+int ekf_device_pointers(ekf_filter* h, void** sigma, int64_t* ld, void** state) {
+    if (!h) return fail(EKF_ERR_INVALID, "null handle");
+    if (sigma) *sigma = h->d_sigma;
+    if (ld) *ld = h->ld;
+    if (state) *state = h->d_state;
+    return EKF_OK;
+}
+int ekf_launch_count(ekf_filter* h, uint64_t* out) {
+    if (!h || !out) return fail(EKF_ERR_INVALID, "null argument");
+    *out = h->launches;
+    return EKF_OK;
+}
+
+}  // extern "C"
+
+// ======================================================================================= batch
+struct ekf_batch {
+    long long B = 0;
+    int n = 0, N = 0, device = 0;
+    int sig_stride = 0, st_stride = 0;
+    cudaStream_t stream = nullptr;       // compute
+    cudaStream_t copy_stream = nullptr;  // H2D of the next step's inputs
+    cudaStream_t out_stream = nullptr;   // D2H of results
+    uint64_t launches = 0;
+    double* d_sigma = nullptr;
+    double* d_state = nullptr;
+    int32_t* d_init_flag = nullptr;
+    uint8_t* d_known = nullptr;
+    unsigned long long* d_nupd = nullptr;
+    // double-buffered device inputs
+    int m_cap = 0;
+    double* d_twists[2] = {nullptr, nullptr};
+    double* d_xy[2] = {nullptr, nullptr};
+    uint8_t* d_vis[2] = {nullptr, nullptr};
+    int32_t* d_count[2] = {nullptr, nullptr};
+    int32_t* d_assoc = nullptr;
+    cudaEvent_t ev_copied[2] = {nullptr, nullptr};
+    cudaEvent_t ev_consumed[2] = {nullptr, nullptr};
+    cudaEvent_t ev_step = nullptr;
+    cudaEvent_t ev_out = nullptr;
+    int slot = 0;
+    double* d_poses = nullptr;
+    double* d_acc4 = nullptr;
+    double* d_truth = nullptr;
+};
+
+namespace {
+
+int free_batch(ekf_batch* b) {
+    if (!b) return EKF_OK;
+    DeviceGuard g(b->device);
+    cudaDeviceSynchronize();
+    cudaFree(b->d_sigma);
+    cudaFree(b->d_state);
+    cudaFree(b->d_init_flag);
+    cudaFree(b->d_known);
+    cudaFree(b->d_nupd);
+    for (int s = 0; s < 2; ++s) {
+        cudaFree(b->d_twists[s]);
+        cudaFree(b->d_xy[s]);
+        cudaFree(b->d_vis[s]);
+        cudaFree(b->d_count[s]);
+        if (b->ev_copied[s]) cudaEventDestroy(b->ev_copied[s]);
+        if (b->ev_consumed[s]) cudaEventDestroy(b->ev_consumed[s]);
+    }
+    cudaFree(b->d_assoc);
+    cudaFree(b->d_poses);
+    cudaFree(b->d_acc4);
+    cudaFree(b->d_truth);
+    if (b->ev_step) cudaEventDestroy(b->ev_step);
+    if (b->ev_out) cudaEventDestroy(b->ev_out);
+    if (b->stream) cudaStreamDestroy(b->stream);
+    if (b->copy_stream) cudaStreamDestroy(b->copy_stream);
+    if (b->out_stream) cudaStreamDestroy(b->out_stream);
+    cudaGetLastError();
+    delete b;
+    return EKF_OK;
+}
+
+int batch_ensure_xy(ekf_batch* b, int m_max) {
+    const int need = std::max(b->n, m_max);
+    if (need <= b->m_cap) return EKF_OK;
+    CU(cudaDeviceSynchronize());
+    for (int s = 0; s < 2; ++s) {
+        cudaFree(b->d_xy[s]);
+        b->d_xy[s] = nullptr;
+        CU(cudaMalloc(&b->d_xy[s], sizeof(double) * 2 * (size_t)need * b->B));
+    }
+    cudaFree(b->d_assoc);
+    b->d_assoc = nullptr;
+    CU(cudaMalloc(&b->d_assoc, sizeof(int32_t) * (size_t)need * b->B));
+    b->m_cap = need;
+    return EKF_OK;
+}
+
+FusedParams batch_params(ekf_batch* b, int mode, int m_max, const double* tw, const double* xy, const uint8_t* vis,
+                         const int32_t* cnt, int32_t* assoc) {
+    FusedParams p;
+    memset(&p, 0, sizeof(p));
+    p.sigma = b->d_sigma;
+    p.state = b->d_state;
+    p.init_flag = b->d_init_flag;
+    p.known = b->d_known;
+    p.twists = tw;
+    p.xy = xy;
+    p.vis = vis;
+    p.mcount = cnt;
+    p.assoc_out = assoc;
+    p.n_updates = b->d_nupd;
+    p.B = b->B;
+    p.n = b->n;
+    p.m_max = m_max;
+    p.mode = mode;
+    p.sig_stride = b->sig_stride;
+    p.st_stride = b->st_stride;
+    return p;
+}
+
+}  // namespace
+
+extern "C" {
+
+int ekf_batch_create(int64_t B, int n, int device, ekf_batch** out) {
+    if (!out) return fail(EKF_ERR_INVALID, "null out pointer");
+    *out = nullptr;
+    if (B <= 0 || n <= 0) return fail(EKF_ERR_INVALID, "invalid batch shape");
+    if (n > kFusedMaxN) return fail(EKF_ERR_UNSUPPORTED, "batched filters use the fused engine: n <= %d", kFusedMaxN);
+    int count = 0;
+    int rc = ekf_device_count(&count);
+    if (rc) return rc;
+    if (device < 0 || device >= count) return fail(EKF_ERR_INVALID, "device %d not available (%d visible)", device, count);
+    DeviceGuard g(device);
+    ekf_batch* b = new (std::nothrow) ekf_batch();
+    if (!b) return fail(EKF_ERR_STATE, "out of host memory");
+    b->B = B;
+    b->n = n;
+    b->N = 3 + 2 * n;
+    b->device = device;
+    b->sig_stride = fused_round16(b->N * b->N);
+    b->st_stride = fused_round16(b->N);
+#define CUB(expr)                          \
+    do {                                   \
+        cudaError_t e_ = (expr);           \
+        if (e_ != cudaSuccess) {           \
+            cudaGetLastError();            \
+            int code_ = fail((int)e_, "%s failed: %s", #expr, cudaGetErrorString(e_)); \
+            free_batch(b);                 \
+            return code_;                  \
+        }                                  \
+    } while (0)
+    CUB(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
+    CUB(cudaStreamCreateWithFlags(&b->copy_stream, cudaStreamNonBlocking));
+    CUB(cudaStreamCreateWithFlags(&b->out_stream, cudaStreamNonBlocking));
+    CUB(cudaMalloc(&b->d_sigma, sizeof(double) * (size_t)b->sig_stride * B));
+    CUB(cudaMalloc(&b->d_state, sizeof(double) * (size_t)b->st_stride * B));
+    CUB(cudaMalloc(&b->d_init_flag, sizeof(int32_t) * (size_t)B));
+    CUB(cudaMalloc(&b->d_known, (size_t)n * B));
+    CUB(cudaMalloc(&b->d_nupd, sizeof(unsigned long long)));
+    CUB(cudaMalloc(&b->d_poses, sizeof(double) * 3 * (size_t)B));
+    CUB(cudaMalloc(&b->d_acc4, sizeof(double) * 4));
+    CUB(cudaMalloc(&b->d_truth, sizeof(double) * 3 * (size_t)B));
+    for (int s = 0; s < 2; ++s) {
+        CUB(cudaMalloc(&b->d_twists[s], sizeof(double) * 2 * (size_t)B));
+        CUB(cudaMalloc(&b->d_vis[s], (size_t)n * B));
+        CUB(cudaMalloc(&b->d_count[s], sizeof(int32_t) * (size_t)B));
+        CUB(cudaEventCreateWithFlags(&b->ev_copied[s], cudaEventDisableTiming));
+        CUB(cudaEventCreateWithFlags(&b->ev_consumed[s], cudaEventDisableTiming));
+    }
+    CUB(cudaEventCreateWithFlags(&b->ev_step, cudaEventDisableTiming));
+    CUB(cudaEventCreateWithFlags(&b->ev_out, cudaEventDisableTiming));
+    CUB(cudaMemsetAsync(b->d_known, 0, (size_t)n * B, b->stream));
+    CUB(cudaMemsetAsync(b->d_nupd, 0, sizeof(unsigned long long), b->stream));
+    if (B > 0x7fffffffLL) {
+        free_batch(b);
+        return fail(EKF_ERR_INVALID, "batch too large");
+    }
+    k_fused_init<<<(unsigned)B, 128, 0, b->stream>>>(b->d_sigma, b->d_state, b->d_init_flag, B, b->N, b->sig_stride,
+                                                     b->st_stride);
+    b->launches += 1;
+    CUB(cudaGetLastError());
+    rc = batch_ensure_xy(b, n);
+    if (rc) {
+        free_batch(b);
+        return rc;
+    }
+    CUB(cudaStreamSynchronize(b->stream));
+#undef CUB
+    *out = b;
+    return EKF_OK;
+}
+
+int ekf_batch_destroy(ekf_batch* b) { return free_batch(b); }
+int64_t ekf_batch_size(const ekf_batch* b) { return b ? b->B : EKF_ERR_INVALID; }
+void* ekf_batch_stream(ekf_batch* b) { return b ? (void*)b->stream : nullptr; }
+
+int ekf_batch_step_known_dev(ekf_batch* b, const double* d_twists, const double* d_xy, const uint8_t* d_visible) {
+    if (!b || !d_twists || !d_xy || !d_visible) return fail(EKF_ERR_INVALID, "null argument");
+    DeviceGuard g(b->device);
+    FusedParams p = batch_params(b, kDoPredict | kDoMeasurement, 1, d_twists, d_xy, d_visible, nullptr, nullptr);
+    int rc = launch_fused(p, b->stream, b->device);
+    b->launches += 1;
+    return rc;
+}
+
+int ekf_batch_step_unknown_dev(ekf_batch* b, const double* d_twists, const double* d_meas, const int32_t* d_count,
+                               int m_max, int32_t* d_assoc_out) {
+    if (!b || !d_twists || !d_meas || m_max <= 0) return fail(EKF_ERR_INVALID, "invalid argument");
+    DeviceGuard g(b->device);
+    FusedParams p = batch_params(b, kDoPredict | kDoAssociation, m_max, d_twists, d_meas, nullptr, d_count, d_assoc_out);
+    int rc = launch_fused(p, b->stream, b->device);
+    b->launches += 1;
+    return rc;
+}
+
+int ekf_batch_step_known(ekf_batch* b, const double* twists, const double* xy, const uint8_t* visible) {
+    if (!b || !twists || !xy || !visible) return fail(EKF_ERR_INVALID, "null argument");
+    DeviceGuard g(b->device);
+    const int s = b->slot;
+    b->slot ^= 1;
+    const size_t B = (size_t)b->B;
+    // the copy stream may overwrite slot s only after the step that last read it has finished
+    CU(cudaStreamWaitEvent(b->copy_stream, b->ev_consumed[s], 0));
+    CU(cudaMemcpyAsync(b->d_twists[s], twists, sizeof(double) * 2 * B, cudaMemcpyHostToDevice, b->copy_stream));
+    CU(cudaMemcpyAsync(b->d_xy[s], xy, sizeof(double) * 2 * b->n * B, cudaMemcpyHostToDevice, b->copy_stream));
+    CU(cudaMemcpyAsync(b->d_vis[s], visible, (size_t)b->n * B, cudaMemcpyHostToDevice, b->copy_stream));
+    CU(cudaEventRecord(b->ev_copied[s], b->copy_stream));
+    CU(cudaStreamWaitEvent(b->stream, b->ev_copied[s], 0));
+    int rc = ekf_batch_step_known_dev(b, b->d_twists[s], b->d_xy[s], b->d_vis[s]);
+    if (rc) return rc;
+    CU(cudaEventRecord(b->ev_consumed[s], b->stream));
+    return EKF_OK;
+}
+
+int ekf_batch_step_unknown(ekf_batch* b, const double* twists, const double* meas, const int32_t* count, int m_max,
+                           int32_t* assoc_out) {
+    if (!b || !twists || !meas || !count || m_max <= 0) return fail(EKF_ERR_INVALID, "invalid argument");
+    DeviceGuard g(b->device);
+    int rc = batch_ensure_xy(b, m_max);
+    if (rc) return rc;
+    const int s = b->slot;
+    b->slot ^= 1;
+    const size_t B = (size_t)b->B;
+    CU(cudaStreamWaitEvent(b->copy_stream, b->ev_consumed[s], 0));
+    CU(cudaMemcpyAsync(b->d_twists[s], twists, sizeof(double) * 2 * B, cudaMemcpyHostToDevice, b->copy_stream));
+    CU(cudaMemcpyAsync(b->d_xy[s], meas, sizeof(double) * 2 * m_max * B, cudaMemcpyHostToDevice, b->copy_stream));
+    CU(cudaMemcpyAsync(b->d_count[s], count, sizeof(int32_t) * B, cudaMemcpyHostToDevice, b->copy_stream));
+    CU(cudaEventRecord(b->ev_copied[s], b->copy_stream));
+    CU(cudaStreamWaitEvent(b->stream, b->ev_copied[s], 0));
+    rc = ekf_batch_step_unknown_dev(b, b->d_twists[s], b->d_xy[s], b->d_count[s], m_max, assoc_out ? b->d_assoc : nullptr);
+    if (rc) return rc;
+    CU(cudaEventRecord(b->ev_consumed[s], b->stream));
+    if (assoc_out) {
+        CU(cudaMemcpyAsync(assoc_out, b->d_assoc, sizeof(int32_t) * m_max * B, cudaMemcpyDeviceToHost, b->stream));
+        CU(cudaStreamSynchronize(b->stream));
+    }
+    return EKF_OK;
+}
+
+int ekf_batch_get_poses_async(ekf_batch* b, double* pinned_out) {
+    if (!b || !pinned_out) return fail(EKF_ERR_INVALID, "null argument");
+    DeviceGuard g(b->device);
+    // gather on the compute stream (ordered after the step), copy out on the output stream
+    CU(cudaStreamWaitEvent(b->stream, b->ev_out, 0));  // previous read-back of d_poses must be done
+    const long long total = 3 * b->B;
+    k_gather_poses<<<(unsigned)((total + 255) / 256), 256, 0, b->stream>>>(b->d_state, b->B, b->st_stride, b->d_poses);
+    b->launches += 1;
+    CU(cudaGetLastError());
+    CU(cudaEventRecord(b->ev_step, b->stream));
+    CU(cudaStreamWaitEvent(b->out_stream, b->ev_step, 0));
+    CU(cudaMemcpyAsync(pinned_out, b->d_poses, sizeof(double) * (size_t)total, cudaMemcpyDeviceToHost, b->out_stream));
+    CU(cudaEventRecord(b->ev_out, b->out_stream));
+    return EKF_OK;
+}
+
+int ekf_batch_get_poses(ekf_batch* b, double* out) {
+    int rc = ekf_batch_get_poses_async(b, out);
+    if (rc) return rc;
+    DeviceGuard g(b->device);
+    CU(cudaStreamSynchronize(b->out_stream));
+    return EKF_OK;
+}
+
+int ekf_batch_get_states(ekf_batch* b, double* out) {
+    if (!b || !out) return fail(EKF_ERR_INVALID, "null argument");
+    DeviceGuard g(b->device);
+    CU(cudaMemcpy2DAsync(out, sizeof(double) * b->N, b->d_state, sizeof(double) * b->st_stride, sizeof(double) * b->N,
+                         (size_t)b->B, cudaMemcpyDeviceToHost, b->stream));
+    CU(cudaStreamSynchronize(b->stream));
+    return EKF_OK;
+}
+
+int ekf_batch_get_sigma(ekf_batch* b, int64_t filter, double* out, int64_t ld) {
+    if (!b || !out || filter < 0 || filter >= b->B || ld < b->N) return fail(EKF_ERR_INVALID, "invalid argument");
+    DeviceGuard g(b->device);
+    CU(cudaMemcpy2DAsync(out, sizeof(double) * ld, b->d_sigma + (size_t)filter * b->sig_stride, sizeof(double) * b->N,
+                         sizeof(double) * b->N, b->N, cudaMemcpyDeviceToHost, b->stream));
+    CU(cudaStreamSynchronize(b->stream));
+    return EKF_OK;
+}
+
+int ekf_batch_get_known(ekf_batch* b, uint8_t* out) {
+    if (!b || !out) return fail(EKF_ERR_INVALID, "null argument");
+    DeviceGuard g(b->device);
+    CU(cudaMemcpyAsync(out, b->d_known, (size_t)b->n * b->B, cudaMemcpyDeviceToHost, b->stream));
+    CU(cudaStreamSynchronize(b->stream));
+    return EKF_OK;
+}
+int ekf_batch_set_known(ekf_batch* b, const uint8_t* in) {
+    if (!b || !in) return fail(EKF_ERR_INVALID, "null argument");
+    DeviceGuard g(b->device);
+    CU(cudaMemcpyAsync(b->d_known, in, (size_t)b->n * b->B, cudaMemcpyHostToDevice, b->stream));
+    CU(cudaStreamSynchronize(b->stream));
+    return EKF_OK;
+}
+int ekf_batch_update_count(ekf_batch* b, uint64_t* out) {
+    if (!b || !out) return fail(EKF_ERR_INVALID, "null argument");
+    DeviceGuard g(b->device);
+    unsigned long long v = 0;
+    CU(cudaMemcpyAsync(&v, b->d_nupd, sizeof(v), cudaMemcpyDeviceToHost, b->stream));
+    CU(cudaStreamSynchronize(b->stream));
+    *out = v;
+    return EKF_OK;
+}
+int ekf_batch_pose_error(ekf_batch* b, const double* truth, double* out4) {
+    if (!b || !truth || !out4) return fail(EKF_ERR_INVALID, "null argument");
+    DeviceGuard g(b->device);
+    CU(cudaMemcpyAsync(b->d_truth, truth, sizeof(double) * 3 * (size_t)b->B, cudaMemcpyHostToDevice, b->stream));
+    CU(cudaMemsetAsync(b->d_acc4, 0, sizeof(double) * 4, b->stream));
+    const int blocks = (int)std::min<long long>((b->B + 255) / 256, 1184);
+    k_pose_error<<<blocks, 256, 0, b->stream>>>(b->d_state, b->B, b->st_stride, b->d_truth, b->d_acc4);
+    b->launches += 1;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(out4, b->d_acc4, sizeof(double) * 4, cudaMemcpyDeviceToHost, b->stream));
+    CU(cudaStreamSynchronize(b->stream));
+    out4[3] = (double)b->B;
+    return EKF_OK;
+}
+int ekf_batch_sync(ekf_batch* b) {
+    if (!b) return fail(EKF_ERR_INVALID, "null handle");
+    DeviceGuard g(b->device);
+    CU(cudaStreamSynchronize(b->copy_stream));
+    CU(cudaStreamSynchronize(b->stream));
+    CU(cudaStreamSynchronize(b->out_stream));
+    return EKF_OK;
+}
+int ekf_batch_device_pointers(ekf_batch* b, void** sigma, int64_t* sigma_stride, void** state, int64_t* state_stride) {
+    if (!b) return fail(EKF_ERR_INVALID, "null handle");
+    if (sigma) *sigma = b->d_sigma;
+    if (sigma_stride) *sigma_stride = b->sig_stride;
+    if (state) *state = b->d_state;
+    if (state_stride) *state_stride = b->st_stride;
+    return EKF_OK;
+}
+int ekf_batch_launch_count(ekf_batch* b, uint64_t* out) {
+    if (!b || !out) return fail(EKF_ERR_INVALID, "null argument");
+    *out = b->launches;
+    return EKF_OK;
+}
+
+int ekf_normalize_angles(const double* in, double* out, int64_t count, int device) {
+    if (!in || !out || count < 0) return fail(EKF_ERR_INVALID, "invalid argument");
+    if (count == 0) return EKF_OK;
+    int ndev = 0;
+    int rc = ekf_device_count(&ndev);
+    if (rc) return rc;
+    if (device < 0 || device >= ndev) return fail(EKF_ERR_INVALID, "device %d not available", device);
+    DeviceGuard g(device);
+    double *d_in = nullptr, *d_out = nullptr;
+    CU(cudaMalloc(&d_in, sizeof(double) * count));
+    CU(cudaMalloc(&d_out, sizeof(double) * count));
+    CU(cudaMemcpy(d_in, in, sizeof(double) * count, cudaMemcpyHostToDevice));
+    k_normalize<<<(unsigned)((count + 255) / 256), 256>>>(d_in, d_out, count);
+    CU(cudaGetLastError());
+    CU(cudaMemcpy(out, d_out, sizeof(double) * count, cudaMemcpyDeviceToHost));
+    cudaFree(d_in);
+    cudaFree(d_out);
+    return EKF_OK;
+}
+
+// DiffDrive::getBodyTwistForUpdate, rigid2d/src/diff_drive.cpp:38-47 (two multiplies: host arithmetic)
+int ekf_body_twist(double wheel_base, double wheel_radius, double left, double right, double* out2) {
+    if (!out2) return fail(EKF_ERR_INVALID, "null argument");
+    const double D = wheel_base * 0.5, r = wheel_radius;
+    out2[0] = (r / (2.0 * D)) * (right - left);
+    out2[1] = (r / 2.0) * (right + left);
+    return EKF_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,366 @@
+// Engine 1: the whole EKF-SLAM step of one filter (prediction + measurement() or data_association())
+// in ONE kernel, one warp per filter, with Sigma resident in shared memory for all of the step's
+// sequential rank-2 updates.  Sigma and the state are staged HBM -> smem -> HBM with the bulk copy
+// engine (TMA), so per filter and step HBM sees exactly one read and one write of Sigma, however many
+// landmarks are corrected.  Used for the Monte-Carlo batch (B = 65,536 x n = 20) and, with B = 1, for a
+// single reference-sized filter (one launch per API call instead of ~10 launches).
+//
+// Restates rigid2d/src/ekf_slam.cpp:55-106 (prediction), :108-197 (measurement), :200-214
+// (initialize_landmark), :217-276 (calculate_maha_dis), :278-402 (data_association).
+#pragma once
+#include "bulk_copy.cuh"
+#include "ekf_math.cuh"
+
+namespace ekf {
+
+enum FusedMode : int { kDoPredict = 1, kDoMeasurement = 2, kDoAssociation = 4 };
+
+struct FusedParams {
+    double* sigma;         // [B][sig_stride]   row-major N x N per filter, stride padded to 16 doubles
+    double* state;         // [B][st_stride]    theta, x, y, m1x, m1y, ...
+    int32_t* init_flag;    // [B]               landmark_init_flag (ekf_slam.cpp:50)
+    uint8_t* known;        // [B][n]            known_list (data_association only, in/out)
+    const double* twists;  // [B][2]            {dtheta, dx}
+    const double* xy;      // measurement: [B][2n] robot-frame readings; association: [B][m_max][2]
+    const uint8_t* vis;    // [B][n]
+    const int32_t* mcount; // [B]               number of valid measurements (association)
+    int32_t* assoc_out;    // [B][m_max] or null
+    double* dmin_out;      // [B][m_max] or null
+    double* second_out;    // [B][m_max] or null
+    uint8_t* created_out;  // [B][m_max] or null
+    unsigned long long* n_updates;  // running count of landmark corrections, or null
+    long long B;
+    int n;
+    int m_max;
+    int mode;
+    int sig_stride;  // doubles
+    int st_stride;   // doubles
+};
+
+__host__ __device__ inline int fused_round16(int v) { return (v + 15) & ~15; }
+
+// shared memory carve-up (bytes), identical on host and device
+struct FusedSmem {
+    int off_sig, off_st, off_k2, off_w2, off_z, off_bar, total;
+    __host__ __device__ FusedSmem(int n, int m_max) {
+        const int N = 3 + 2 * n;
+        int o = 0;
+        off_sig = o;
+        o += fused_round16(N * N) * 8;
+        off_st = o;
+        o += fused_round16(N) * 8;
+        off_k2 = o;
+        o += fused_round16(2 * N) * 8;
+        off_w2 = o;
+        o += fused_round16(2 * N) * 8;
+        off_z = o;
+        const int zc = 2 * (n > m_max ? n : m_max);
+        o += fused_round16(zc) * 8;
+        off_bar = o;
+        o += 16;
+        total = o;
+    }
+};
+
+// One landmark correction on the smem-resident filter (ekf_slam.cpp:138-192 == :335-390).
+// All lanes enter with identical (i, zr, zphi, theta, x, y).
+template <int NL>
+__device__ __forceinline__ void warp_correct(double* __restrict__ sig, double* __restrict__ st,
+                                             double2* __restrict__ K2, double2* __restrict__ W2, const int N,
+                                             const int lane, const int i, const double zr, const double zphi,
+                                             const double theta, const double x, const double y) {
+    const int i3 = 3 + 2 * i, i4 = i3 + 1;
+    const Hj h = make_hj(st[i3], st[i4], theta, x, y);
+
+    // W = Hj * Sigma (2 x N, from 5 rows) and P = Sigma * Hj^T (N x 2, from 5 columns)
+    for (int c = lane; c < N; c += 32) {
+        const double s0 = sig[c], s1 = sig[N + c], s2 = sig[2 * N + c];
+        const double s3 = sig[i3 * N + c], s4 = sig[i4 * N + c];
+        W2[c] = make_double2(h_row0(h, s1, s2, s3, s4), h_row1(h, s0, s1, s2, s3, s4));
+        const double* row = sig + c * N;
+        const double r0 = row[0], r1 = row[1], r2 = row[2], r3 = row[i3], r4 = row[i4];
+        K2[c] = make_double2(h_row0(h, r1, r2, r3, r4), h_row1(h, r0, r1, r2, r3, r4));
+    }
+    __syncwarp();
+    // S = (Hj Sigma) Hj^T + R from W at the five columns; closed-form inverse
+    const double2 w0 = W2[0], w1 = W2[1], w2 = W2[2], w3 = W2[i3], w4 = W2[i4];
+    const double s00 = h_row0(h, w1.x, w2.x, w3.x, w4.x) + kR;
+    const double s01 = h_row1(h, w0.x, w1.x, w2.x, w3.x, w4.x);
+    const double s10 = h_row0(h, w1.y, w2.y, w3.y, w4.y);
+    const double s11 = h_row1(h, w0.y, w1.y, w2.y, w3.y, w4.y) + kR;
+    const Sym2 si = inv2x2(s00, s01, s10, s11);
+    const double nu0 = __dsub_rn(zr, h.zr);
+    const double nu1 = normalize_angle(__dsub_rn(zphi, h.zphi));  // :182-183
+    // K = P S^-1; state += K nu
+    for (int r = lane; r < N; r += 32) {
+        const double2 p = K2[r];
+        const double k0 = fma(p.y, si.i10, p.x * si.i00);
+        const double k1 = fma(p.y, si.i11, p.x * si.i01);
+        K2[r] = make_double2(k0, k1);
+        st[r] = st[r] + fma(k1, nu1, k0 * nu0);
+    }
+    __syncwarp();
+    if (lane == 0) st[0] = normalize_angle(st[0]);  // :187
+    // Sigma <- (I - K Hj) Sigma = Sigma - K W   (:191-192), in place in shared memory
+    {
+        constexpr int NC = NL ? 3 + 2 * NL : 0;
+        const int main_cols = N < 32 ? N : 32;
+        if (lane < main_cols) {
+            const double2 w = W2[lane];
+            double* p = sig + lane;
+            if (NC) {
+#pragma unroll
+                for (int r = 0; r < NC; ++r) {
+                    const double2 k = K2[r];
+                    p[r * NC] = fma(-k.y, w.y, fma(-k.x, w.x, p[r * NC]));
+                }
+            } else {
+                for (int r = 0; r < N; ++r) {
+                    const double2 k = K2[r];
+                    p[r * N] = fma(-k.y, w.y, fma(-k.x, w.x, p[r * N]));
+                }
+            }
+        }
+        const int rc = N - 32;  // remainder columns [32, N)
+        if (rc > 0) {
+            const int total = N * rc;
+            for (int e = lane; e < total; e += 32) {
+                const int r = e / rc, c = 32 + (e - r * rc);
+                const double2 k = K2[r];
+                const double2 w = W2[c];
+                double* q = sig + r * N + c;
+                *q = fma(-k.y, w.y, fma(-k.x, w.x, *q));
+            }
+        }
+    }
+    __syncwarp();
+}
+
+template <int NL>
+__global__ void __launch_bounds__(32) ekf_fused_kernel(const FusedParams p) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int n = NL ? NL : p.n;
+    const int N = 3 + 2 * n;
+    const FusedSmem L(n, p.m_max);
+    double* sig = reinterpret_cast<double*>(smem_raw + L.off_sig);
+    double* st = reinterpret_cast<double*>(smem_raw + L.off_st);
+    double2* K2 = reinterpret_cast<double2*>(smem_raw + L.off_k2);
+    double2* W2 = reinterpret_cast<double2*>(smem_raw + L.off_w2);
+    double* zbuf = reinterpret_cast<double*>(smem_raw + L.off_z);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + L.off_bar);
+
+    const int lane = threadIdx.x;
+    const long long b = blockIdx.x;
+    if (b >= p.B) return;
+    double* g_sig = p.sigma + b * (long long)p.sig_stride;
+    double* g_st = p.state + b * (long long)p.st_stride;
+    const uint32_t sig_bytes = (uint32_t)p.sig_stride * 8u, st_bytes = (uint32_t)p.st_stride * 8u;
+
+    // ---- stage Sigma and the state into shared memory with the bulk copy engine
+    if (lane == 0) {
+        mbar_init(bar, 1);
+        fence_mbar_init();
+        mbar_arrive_expect_tx(bar, sig_bytes + st_bytes);
+        bulk_g2s(sig, g_sig, sig_bytes, bar);
+        bulk_g2s(st, g_st, st_bytes, bar);
+    }
+    // inputs that do not depend on the filter state are fetched while the copy is in flight
+    double dtheta = 0.0, dxv = 0.0;
+    if (p.mode & kDoPredict) {
+        dtheta = p.twists[2 * b];
+        dxv = p.twists[2 * b + 1];
+    }
+    int init_flag = p.init_flag[b];
+    unsigned vis_mask_lo = 0;  // generic n handled through zbuf flags below
+    int m = 0;
+    if (p.mode & kDoMeasurement) {
+        // z = (range, bearing) of every slot's reading, lane-parallel (ekf_slam.cpp:140-146)
+        for (int i = lane; i < n; i += 32) {
+            const double sx = p.xy[b * 2 * n + 2 * i], sy = p.xy[b * 2 * n + 2 * i + 1];
+            double r, phi;
+            range_bearing(sx, sy, r, phi);
+            zbuf[2 * i] = r;
+            zbuf[2 * i + 1] = phi;
+        }
+    } else if (p.mode & kDoAssociation) {
+        m = p.mcount ? p.mcount[b] : p.m_max;
+        m = m < p.m_max ? m : p.m_max;
+        for (int j = lane; j < m; j += 32) {
+            const double sx = p.xy[(b * p.m_max + j) * 2], sy = p.xy[(b * p.m_max + j) * 2 + 1];
+            double r, phi;
+            range_bearing(sx, sy, r, phi);
+            zbuf[2 * j] = r;
+            zbuf[2 * j + 1] = phi;
+        }
+    }
+    (void)vis_mask_lo;
+    __syncwarp();
+    mbar_wait(bar, 0);
+
+    // ---- prediction (ekf_slam.cpp:55-106): rows 1,2 += a*row0; cols 1,2 += a*col0; Q on the diagonal
+    if (p.mode & kDoPredict) {
+        const Motion mo = motion_model(st[0], dtheta, dxv);
+        __syncwarp();
+        for (int c = lane; c < N; c += 32) {
+            const double r0 = sig[c];
+            sig[N + c] = fma(mo.a1, r0, sig[N + c]);
+            sig[2 * N + c] = fma(mo.a2, r0, sig[2 * N + c]);
+        }
+        __syncwarp();
+        for (int r = lane; r < N; r += 32) {
+            const double c0 = sig[r * N];
+            sig[r * N + 1] = fma(c0, mo.a1, sig[r * N + 1]);
+            sig[r * N + 2] = fma(c0, mo.a2, sig[r * N + 2]);
+        }
+        __syncwarp();
+        if (lane == 0) {
+            sig[0] += kQ;
+            sig[N + 1] += kQ;
+            sig[2 * N + 2] += kQ;
+            st[0] = st[0] + mo.u0;  // theta is not wrapped here (:99)
+            st[1] = st[1] + mo.u1;
+            st[2] = st[2] + mo.u2;
+        }
+        __syncwarp();
+    }
+
+    unsigned long long n_corr = 0;
+
+    // ---- measurement(): known association (ekf_slam.cpp:108-197)
+    if (p.mode & kDoMeasurement) {
+        const double theta = st[0], x = st[1], y = st[2];  // read once; stale for later i (:109-111)
+        if (!init_flag) {
+            for (int i = lane; i < n; i += 32) {
+                double mx, my;
+                landmark_from_reading(p.xy[b * 2 * n + 2 * i], p.xy[b * 2 * n + 2 * i + 1], theta, x, y, mx, my);
+                st[3 + 2 * i] = mx;
+                st[4 + 2 * i] = my;
+            }
+            init_flag = 1;
+            __syncwarp();
+        }
+        const uint8_t* vis = p.vis + b * n;
+        for (int base = 0; base < n; base += 32) {
+            const int i_l = base + lane;
+            const unsigned mask = __ballot_sync(0xffffffffu, i_l < n && vis[i_l] != 0);
+            unsigned rem = mask;
+            while (rem) {
+                const int i = base + __ffs(rem) - 1;
+                rem &= rem - 1;
+                warp_correct<NL>(sig, st, K2, W2, N, lane, i, zbuf[2 * i], zbuf[2 * i + 1], theta, x, y);
+                ++n_corr;
+            }
+        }
+    }
+
+    // ---- data_association(): Mahalanobis nearest neighbour + landmark initialisation (ekf_slam.cpp:278-402)
+    if (p.mode & kDoAssociation) {
+        uint8_t* known = p.known + b * n;
+        int known_count = 0;  // leading-true prefix (:281-288)
+        for (int base = 0; base < n; base += 32) {
+            const int i_l = base + lane;
+            const unsigned ones = __ballot_sync(0xffffffffu, i_l < n && known[i_l] != 0);
+            const int lead = __ffs(~ones) - 1;  // number of leading ones in this group of 32 (32 -> -1)
+            if (ones == 0xffffffffu) {
+                known_count += 32;
+                continue;
+            }
+            known_count += lead;
+            break;
+        }
+        if (known_count > n) known_count = n;
+        const int known_count0 = known_count;
+        for (int j = 0; j < m; ++j) {
+            const double zr = zbuf[2 * j], zphi = zbuf[2 * j + 1];
+            const double theta = st[0], x = st[1], y = st[2];  // live pose (:219-221)
+            double best = INFINITY, second = INFINITY;
+            int best_i = 0x7fffffff;
+            for (int i = lane; i < known_count; i += 32) {
+                double d = maha_distance(sig, N, i, st[3 + 2 * i], st[4 + 2 * i], zr, zphi, theta, x, y);
+                if (!(d == d)) d = INFINITY;  // NaN never wins
+                if (d < best) {
+                    second = best;
+                    best = d;
+                    best_i = i;
+                } else if (d < second) {
+                    second = d;
+                }
+            }
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                const double ob = __shfl_xor_sync(0xffffffffu, best, off);
+                const double os = __shfl_xor_sync(0xffffffffu, second, off);
+                const int oi = __shfl_xor_sync(0xffffffffu, best_i, off);
+                if (better(ob, oi, best, best_i)) {
+                    second = fmin(best, os);
+                    best = ob;
+                    best_i = oi;
+                } else {
+                    second = fmin(second, ob);
+                }
+            }
+            double min_d = kGateNew;
+            int min_idx = known_count;
+            if (best < kGateNew) {  // d < min_maha_dis, :305
+                min_d = best;
+                min_idx = best_i;
+                second = fmin(second, kGateNew);
+            } else {
+                second = best;
+            }
+            const long long o = b * p.m_max + j;
+            if (lane == 0) {
+                if (p.dmin_out) p.dmin_out[o] = min_d;
+                if (p.second_out) p.second_out[o] = second;
+            }
+            int created = 0;
+            if (min_idx == known_count && min_idx < n) {  // :318-327
+                if (lane == 0) {
+                    double mx, my;
+                    landmark_from_reading(p.xy[o * 2], p.xy[o * 2 + 1], theta, x, y, mx, my);
+                    st[3 + 2 * min_idx] = mx;
+                    st[4 + 2 * min_idx] = my;
+                }
+                __syncwarp();
+                known_count++;
+                min_d = 0.0;
+                created = 1;
+            }
+            int assoc = -1;
+            if (min_d < kGateUpdate) {  // :330
+                warp_correct<NL>(sig, st, K2, W2, N, lane, min_idx, zr, zphi, st[0], st[1], st[2]);
+                ++n_corr;
+                assoc = min_idx;
+            }
+            if (lane == 0) {
+                if (p.assoc_out) p.assoc_out[o] = assoc;
+                if (p.created_out) p.created_out[o] = (uint8_t)created;
+            }
+        }
+        for (int i = known_count0 + lane; i < known_count; i += 32) known[i] = 1;
+        if (lane == 0) {  // outputs beyond the valid count are defined too
+            for (int j = m; j < p.m_max; ++j) {
+                const long long o = b * p.m_max + j;
+                if (p.assoc_out) p.assoc_out[o] = -1;
+                if (p.created_out) p.created_out[o] = 0;
+                if (p.dmin_out) p.dmin_out[o] = kGateNew;
+                if (p.second_out) p.second_out[o] = INFINITY;
+            }
+        }
+    }
+
+    // ---- write back: smem -> HBM with the bulk copy engine
+    __syncwarp();
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+        bulk_s2g(g_sig, sig, sig_bytes);
+        bulk_s2g(g_st, st, st_bytes);
+        bulk_commit();
+        p.init_flag[b] = init_flag;
+        if (p.n_updates && n_corr) atomicAdd(p.n_updates, n_corr);
+        bulk_wait_all();
+    }
+}
+
+}  // namespace ekf

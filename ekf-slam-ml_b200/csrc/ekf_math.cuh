@@ -1,0 +1,180 @@
+// Scalar building blocks of the EKF-SLAM hot path, shared by every engine (fused on-chip filter,
+// streamed large map, row-sharded map).  fp64 throughout, to match the reference's Armadillo doubles.
+//
+// The geometry (z_hat, H_j, 2x2 inverse) is written with explicit round-to-nearest intrinsics so that
+// nvcc does not contract a*b+c into an FMA there: the reference's x86-64 build rounds twice, and keeping
+// the same rounding in the O(1) part of each update costs nothing.  The O(N) / O(N^2) parts use FMAs.
+//
+// Reference lines are relative to /root/reference/rigid2d/src/.
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+namespace ekf {
+
+constexpr double kPi = 3.14159265358979323846;  // rigid2d.hpp:13
+constexpr double kTwoPi = 2.0 * kPi;
+constexpr double kR = 0.01;      // measurement noise, ekf_slam.cpp:172-175
+constexpr double kQ = 0.0001;    // process noise on (theta, x, y), ekf_slam.cpp:41-43
+constexpr double kSigma0 = 100;  // initial landmark variance, ekf_slam.cpp:32
+constexpr double kGateNew = 10.0;    // ekf_slam.cpp:293
+constexpr double kGateUpdate = 1.0;  // ekf_slam.cpp:330
+constexpr double kSmallTurn = 0.000001;  // ekf_slam.cpp:79
+
+// fmod(x, 2*pi), exact like the C library's: the quotient is small on this path, so one FMA recovers the
+// remainder exactly (x and q*2pi are both multiples of ulp(2pi) once |x| >= 2pi, and the remainder is
+// below 8 so it fits 53 bits).  Falls back to fmod() for large or non-finite arguments.
+__device__ __forceinline__ double fmod_2pi(double x) {
+    const double y = kTwoPi;
+    const double ax = fabs(x);
+    if (ax < y) return x;
+    if (!(ax < 1.0e6)) return fmod(x, y);
+    double q = trunc(ax * (1.0 / kTwoPi));
+    double r = fma(-q, y, ax);
+    if (r < 0.0) {
+        q -= 1.0;
+        r = fma(-q, y, ax);
+    } else if (r >= y) {
+        q += 1.0;
+        r = fma(-q, y, ax);
+    }
+    return copysign(r, x);
+}
+
+// rigid2d::normalize_angle, rigid2d.cpp:336-345 -> (-pi, pi]
+__device__ __forceinline__ double normalize_angle(double rad) {
+    const double reduced = fmod_2pi(rad);
+    double ang = fmod_2pi(__dadd_rn(reduced, kTwoPi));
+    if (ang > kPi) ang = __dsub_rn(ang, kTwoPi);
+    return ang;
+}
+
+// Range / bearing of a robot-frame point (ekf_slam.cpp:140-146, 227-233, 338-344).
+__device__ __forceinline__ void range_bearing(double sx, double sy, double& r, double& phi) {
+    r = sqrt(__dadd_rn(__dmul_rn(sx, sx), __dmul_rn(sy, sy)));
+    phi = atan2(sy, sx);
+}
+
+// World position of a landmark seen at robot-frame (sx, sy): ekf_slam.cpp:113-128, 200-214.
+__device__ __forceinline__ void landmark_from_reading(double sx, double sy, double theta, double x, double y,
+                                                      double& mx, double& my) {
+    double r, phi;
+    range_bearing(sx, sy, r, phi);
+    double s, c;
+    sincos(__dadd_rn(phi, theta), &s, &c);
+    mx = __dadd_rn(x, __dmul_rn(r, c));
+    my = __dadd_rn(y, __dmul_rn(r, s));
+}
+
+// The five non-zero columns {0,1,2,3+2i,4+2i} of H_j and the predicted measurement
+// (ekf_slam.cpp:150-170).  h[0][0] == 0 and h[1][0] == -1 are implied and not stored:
+//   row 0: [0, a, b, -a, -b]   a = -dx/sqrt(d), b = -dy/sqrt(d)
+//   row 1: [-1, e, f, -e, -f]  e =  dy/d,       f = -dx/d
+struct Hj {
+    double a, b, e, f;
+    double zr, zphi;  // z_hat
+};
+
+__device__ __forceinline__ Hj make_hj(double mx, double my, double theta, double x, double y) {
+    Hj h;
+    const double dx = __dsub_rn(mx, x), dy = __dsub_rn(my, y);
+    const double d = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+    const double sq = sqrt(d);
+    h.zr = sq;
+    h.zphi = normalize_angle(__dsub_rn(atan2(dy, dx), theta));
+    h.a = -(dx / sq);
+    h.b = -(dy / sq);
+    h.e = dy / d;
+    h.f = -(dx / d);
+    return h;
+}
+
+// Rows of H applied to five gathered values s0..s4 (values at indices 0,1,2,3+2i,4+2i).
+__device__ __forceinline__ double h_row0(const Hj& h, double s1, double s2, double s3, double s4) {
+    return fma(-h.b, s4, fma(-h.a, s3, fma(h.b, s2, h.a * s1)));
+}
+__device__ __forceinline__ double h_row1(const Hj& h, double s0, double s1, double s2, double s3, double s4) {
+    return fma(-h.f, s4, fma(-h.e, s3, fma(h.f, s2, fma(h.e, s1, -s0))));
+}
+
+struct Sym2 {
+    double i00, i01, i10, i11;
+};
+
+// (S)^-1 with Armadillo's closed form for 2x2 ([d -b; -c a] / det); S = [s00 s01; s10 s11].
+__device__ __forceinline__ Sym2 inv2x2(double s00, double s01, double s10, double s11) {
+    const double det = __dsub_rn(__dmul_rn(s00, s11), __dmul_rn(s01, s10));
+    Sym2 r;
+    r.i00 = s11 / det;
+    r.i01 = -s01 / det;
+    r.i10 = -s10 / det;
+    r.i11 = s00 / det;
+    return r;
+}
+
+// Mahalanobis distance of measurement (zr, zphi) to landmark i, from the 5x5 block Sigma[idx, idx]
+// (ekf_slam.cpp:217-276).  The bearing innovation is NOT wrapped (:269).  `sig` may point to shared or
+// global memory; ld is the row stride in doubles.
+__device__ __forceinline__ double maha_distance(const double* __restrict__ sig, int64_t ld, int i, double mx,
+                                                double my, double zr, double zphi, double theta, double x,
+                                                double y) {
+    const Hj h = make_hj(mx, my, theta, x, y);
+    const int64_t id[5] = {0, 1, 2, 3 + 2 * (int64_t)i, 4 + 2 * (int64_t)i};
+    double wl0[5], wl1[5];
+#pragma unroll
+    for (int l = 0; l < 5; ++l) {
+        const double s0 = sig[id[0] * ld + id[l]];
+        const double s1 = sig[id[1] * ld + id[l]];
+        const double s2 = sig[id[2] * ld + id[l]];
+        const double s3 = sig[id[3] * ld + id[l]];
+        const double s4 = sig[id[4] * ld + id[l]];
+        wl0[l] = h_row0(h, s1, s2, s3, s4);
+        wl1[l] = h_row1(h, s0, s1, s2, s3, s4);
+    }
+    // psi = (H Sigma) H^T + R
+    const double p00 = h_row0(h, wl0[1], wl0[2], wl0[3], wl0[4]) + kR;
+    const double p01 = h_row1(h, wl0[0], wl0[1], wl0[2], wl0[3], wl0[4]);
+    const double p10 = h_row0(h, wl1[1], wl1[2], wl1[3], wl1[4]);
+    const double p11 = h_row1(h, wl1[0], wl1[1], wl1[2], wl1[3], wl1[4]) + kR;
+    const Sym2 pi = inv2x2(p00, p01, p10, p11);
+    const double v0 = __dsub_rn(zr, h.zr), v1 = __dsub_rn(zphi, h.zphi);
+    const double t0 = __dadd_rn(__dmul_rn(v0, pi.i00), __dmul_rn(v1, pi.i10));
+    const double t1 = __dadd_rn(__dmul_rn(v0, pi.i01), __dmul_rn(v1, pi.i11));
+    return __dadd_rn(__dmul_rn(t0, v0), __dmul_rn(t1, v1));
+}
+
+// Motion model increments and Jacobian entries (ekf_slam.cpp:67-96): state[0..2] += u, A(1,0)=a1, A(2,0)=a2.
+struct Motion {
+    double u0, u1, u2, a1, a2;
+};
+__device__ __forceinline__ Motion motion_model(double theta, double dtheta, double dx) {
+    Motion m;
+    double s, c;
+    sincos(theta, &s, &c);
+    if (fabs(dtheta) < kSmallTurn) {
+        m.u0 = 0.0;
+        m.u1 = __dmul_rn(dx, c);
+        m.u2 = __dmul_rn(dx, s);
+        m.a1 = __dmul_rn(-dx, s);
+        m.a2 = __dmul_rn(dx, c);
+    } else {
+        double s2, c2;
+        sincos(__dadd_rn(theta, dtheta), &s2, &c2);
+        const double q = dx / dtheta;
+        m.u0 = dtheta;
+        m.u1 = __dadd_rn(__dmul_rn(-q, s), __dmul_rn(q, s2));
+        m.u2 = __dsub_rn(__dmul_rn(q, c), __dmul_rn(q, c2));
+        m.a1 = __dadd_rn(__dmul_rn(-q, c), __dmul_rn(q, c2));
+        m.a2 = __dadd_rn(__dmul_rn(-q, s), __dmul_rn(q, s2));
+    }
+    return m;
+}
+
+// Lexicographic (distance, index) minimum used by the association argmin: strict '<' on distance,
+// lowest index on ties (ekf_slam.cpp:300-309).  NaNs must be mapped to +inf by the caller.
+__device__ __forceinline__ bool better(double d_a, int i_a, double d_b, int i_b) {
+    return (d_a < d_b) || (d_a == d_b && i_a < i_b);
+}
+
+}  // namespace ekf

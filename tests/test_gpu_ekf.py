@@ -1,0 +1,251 @@
+"""GPU parity: the CUDA EKF-SLAM path (through the C ABI) against the CPU oracle on identical seeded inputs.
+
+Bar (BASELINE.json north_star): association indices / landmark counts bit-exact away from threshold ties;
+state and covariance within 1e-9 in the scaled metric of tests/_oracle.py (sigma_err / state_err)."""
+import numpy as np
+import pytest
+
+from _oracle import OracleEKF, sigma_err, state_err
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-9
+
+
+def _trace(pkg, n_slots, steps, seed, world=None):
+    tg = pkg.tracegen
+    w = world or (tg.default_world(n_slots) if n_slots >= 10 else None)
+    return tg.simulate_known(w, 1, steps, seed=seed)
+
+
+def _run_known(filt, oracle, tr, check_every=1):
+    worst_s = worst_x = 0.0
+    T = tr["twists"].shape[0]
+    for t in range(T):
+        dth, dx = tr["twists"][t, 0]
+        filt.prediction((dth, dx))
+        oracle.prediction(dth, dx)
+        filt.measurement(tr["xy"][t, 0], tr["vis"][t, 0])
+        oracle.measurement(tr["xy"][t, 0], tr["vis"][t, 0])
+        if t % check_every == 0 or t == T - 1:
+            worst_x = max(worst_x, state_err(filt.state, oracle.state))
+            worst_s = max(worst_s, sigma_err(filt.sigma, oracle.sigma))
+    return worst_x, worst_s
+
+
+@pytest.mark.parametrize("engine", ["fused", "stream"])
+def test_known_association_default_world(gpu_pkg, engine):
+    """cfg1: nuslam known association on the default 10-tube world, n = 20 slots."""
+    eng = gpu_pkg.ENGINE_FUSED if engine == "fused" else gpu_pkg.ENGINE_STREAM
+    tr = _trace(gpu_pkg, 20, 150, seed=11)
+    f = gpu_pkg.EKF_SLAM(20, engine=eng)
+    o = OracleEKF(20)
+    ex, es = _run_known(f, o, tr, check_every=10)
+    assert f.init_flag and o.init_flag
+    assert f.update_count == int(tr["vis"].sum())
+    assert ex < TOL and es < TOL, (ex, es)
+
+
+@pytest.mark.parametrize("n,engine", [(3, "fused"), (14, "fused"), (33, "fused"), (64, "fused"), (33, "stream"),
+                                      (100, "stream")])
+def test_known_association_other_sizes(gpu_pkg, n, engine):
+    """Generic-n code paths (the n=20 kernel is a specialised instantiation)."""
+    eng = gpu_pkg.ENGINE_FUSED if engine == "fused" else gpu_pkg.ENGINE_STREAM
+    rng = np.random.default_rng(n)
+    lm = rng.uniform(-1.5, 1.5, (n, 2))
+    f = gpu_pkg.EKF_SLAM(n, engine=eng)
+    o = OracleEKF(n)
+    worst = 0.0
+    for t in range(25):
+        dth, dx = 0.05 + rng.normal(0, 0.01), 0.01 + rng.normal(0, 0.002)
+        if t % 7 == 3:
+            dth = 1e-8  # straight-line branch of the motion model (ekf_slam.cpp:79)
+        f.prediction((dth, dx))
+        o.prediction(dth, dx)
+        th, x, y = o.state[:3]
+        rel = lm - [x, y]
+        c, s = np.cos(-th), np.sin(-th)
+        xy = np.stack([c * rel[:, 0] - s * rel[:, 1], s * rel[:, 0] + c * rel[:, 1]], 1) + rng.normal(0, 0.005, (n, 2))
+        vis = (np.hypot(rel[:, 0], rel[:, 1]) < 1.0).astype(np.uint8) if t > 0 else np.zeros(n, np.uint8)
+        f.measurement(xy.ravel(), vis)
+        o.measurement(xy.ravel(), vis)
+        worst = max(worst, state_err(f.state, o.state), sigma_err(f.sigma, o.sigma))
+    assert worst < TOL, worst
+
+
+def _unknown_run(gpu_pkg, n, eng, steps, seed, n_tubes=None):
+    tg = gpu_pkg.tracegen
+    w = tg.default_world(n)
+    if n_tubes:
+        w = tg.dense_world(n_tubes)
+        w.n_slots = n
+    tr = tg.simulate_unknown(w, 1, steps, seed=seed)
+    f = gpu_pkg.EKF_SLAM(n, engine=eng)
+    o = OracleEKF(n)
+    kf = np.zeros(n, np.uint8)
+    ko = np.zeros(n, np.uint8)
+    worst = 0.0
+    n_meas = n_tie = 0
+    for t in range(steps):
+        dth, dx = tr["twists"][t, 0]
+        f.prediction((dth, dx))
+        o.prediction(dth, dx)
+        m = int(tr["count"][t, 0])
+        meas = tr["meas"][t, 0, :m]
+        res = f.data_association(meas, kf)
+        a_o, dmin_o, sec_o, cr_o = o.data_association(meas, ko)
+        # a decision is "away from a tie" when neither gate nor the runner-up is within 1e-6 (relative) of dmin
+        margin = np.minimum.reduce([np.abs(dmin_o - 10.0), np.abs(dmin_o - 1.0), np.abs(sec_o - dmin_o)])
+        clear = margin > 1e-6 * np.maximum(1.0, np.abs(dmin_o))
+        n_meas += m
+        n_tie += int((~clear).sum())
+        assert np.array_equal(res["assoc"][clear], a_o[clear]), (t, res["assoc"], a_o)
+        assert np.array_equal(res["created"][clear], cr_o[clear])
+        assert np.array_equal(kf, ko), (t, kf, ko)
+        np.testing.assert_allclose(res["dmin"], dmin_o, rtol=1e-7, atol=1e-9)
+        worst = max(worst, state_err(f.state, o.state), sigma_err(f.sigma, o.sigma))
+    return worst, n_meas, n_tie, int(ko.sum())
+
+
+@pytest.mark.parametrize("engine", ["fused", "stream"])
+def test_unknown_association(gpu_pkg, engine):
+    """cfg2 filter side: Mahalanobis gating + landmark initialisation, n = 20 slots, 10 tubes."""
+    eng = gpu_pkg.ENGINE_FUSED if engine == "fused" else gpu_pkg.ENGINE_STREAM
+    worst, n_meas, n_tie, known = _unknown_run(gpu_pkg, 20, eng, 120, seed=5)
+    assert n_meas > 300 and known >= 5
+    assert n_tie == 0
+    assert worst < TOL, worst
+
+
+def test_unknown_association_map_full(gpu_pkg):
+    """More tubes (20) than slots (8): once the map is full unmatched measurements are dropped (ekf_slam.cpp:318)."""
+    worst, n_meas, n_tie, known = _unknown_run(gpu_pkg, 8, gpu_pkg.ENGINE_FUSED, 60, seed=9, n_tubes=20)
+    assert known == 8
+    assert worst < TOL, worst
+
+
+def test_maha_seam_and_getters(gpu_pkg):
+    tr = _trace(gpu_pkg, 20, 30, seed=2)
+    f = gpu_pkg.EKF_SLAM(20)
+    o = OracleEKF(20)
+    _run_known(f, o, tr, check_every=100)
+    for i in (0, 3, 9):
+        d_f = f.calculate_maha_dis((0.3, -0.2), i)
+        d_o = o.maha(0.3, -0.2, i)
+        assert abs(d_f - d_o) <= 1e-9 * max(1.0, abs(d_o))
+    s = o.state
+    assert abs(f.getStateTheta() - s[0]) < 1e-12 and abs(f.getStateX() - s[1]) < 1e-12
+    assert f.getStateLandmark().shape == (40, 1)
+    g = f.clone()
+    assert np.array_equal(g.state, f.state) and np.array_equal(g.sigma, f.sigma)
+
+
+def test_normalize_angle_device_twin_is_bit_exact(gpu_pkg):
+    """rigid2d::normalize_angle: the device twin must equal the C library fmod formulation bit for bit."""
+    import ctypes
+    from _oracle import oracle_lib
+    L = oracle_lib()
+    rng = np.random.default_rng(0)
+    vals = np.concatenate([rng.uniform(-40, 40, 20000), rng.uniform(-7, 7, 20000),
+                           np.array([0.0, -0.0, np.pi, -np.pi, 2 * np.pi, -2 * np.pi, 3 * np.pi, 1e-300, 6.283185307179586,
+                                     6.2831853071795862, 12.566370614359172, 1e5, -1e5, 1e7, -3e9]),
+                           np.nextafter(np.pi * np.arange(-8, 9), np.inf), np.nextafter(np.pi * np.arange(-8, 9), -np.inf)])
+    got = gpu_pkg.normalize_angle(vals)
+    want = np.array([L.oracle_normalize_angle(float(v)) for v in vals])
+    assert np.array_equal(got.view(np.uint64), want.view(np.uint64))
+    # golden values of rigid2d/tests/tests.cpp:322-331
+    g = gpu_pkg.normalize_angle(np.deg2rad([30.0, 230.0, -330.0]))
+    np.testing.assert_allclose(g, [0.523599, -2.26893, 0.523599], rtol=1.2e-5)
+
+
+def test_batch_matches_per_filter_oracle(gpu_pkg):
+    """cfg3 in miniature: every filter of a batch equals its own oracle run (known association)."""
+    tg = gpu_pkg.tracegen
+    B, T = 96, 24
+    tr = tg.simulate_known(tg.dense_world(20), B, T, seed=3)
+    bt = gpu_pkg.EKFBatch(B, 20)
+    for t in range(T):
+        bt.step_known(np.ascontiguousarray(tr["twists"][t]), np.ascontiguousarray(tr["xy"][t]),
+                      np.ascontiguousarray(tr["vis"][t]))
+        bt.sync()
+    states = bt.states()
+    assert bt.update_count == int(tr["vis"].sum())
+    worst = 0.0
+    for b in range(0, B, 5):
+        o = OracleEKF(20)
+        for t in range(T):
+            o.prediction(*tr["twists"][t, b])
+            o.measurement(tr["xy"][t, b], tr["vis"][t, b])
+        worst = max(worst, state_err(states[b], o.state), sigma_err(bt.sigma(b), o.sigma))
+    assert worst < TOL, worst
+    poses = bt.poses()
+    assert np.array_equal(poses, states[:, :3])
+    err = bt.pose_error(tr["truth"][-1])
+    assert err[3] == B and np.all(err[:3] / B < 0.05 ** 2)
+
+
+def test_batch_unknown_matches_oracle(gpu_pkg):
+    tg = gpu_pkg.tracegen
+    B, T, M = 40, 30, 10
+    tr = tg.simulate_unknown(tg.default_world(20), B, T, seed=4, m_max=M)
+    bt = gpu_pkg.EKFBatch(B, 20)
+    assoc = []
+    for t in range(T):
+        assoc.append(bt.step_unknown(np.ascontiguousarray(tr["twists"][t]), np.ascontiguousarray(tr["meas"][t]),
+                                     np.ascontiguousarray(tr["count"][t]), M, want_assoc=True))
+    states, known = bt.states(), bt.known
+    worst = 0.0
+    for b in range(0, B, 3):
+        o = OracleEKF(20)
+        k = np.zeros(20, np.uint8)
+        for t in range(T):
+            o.prediction(*tr["twists"][t, b])
+            m = int(tr["count"][t, b])
+            a, _, _, _ = o.data_association(tr["meas"][t, b, :m], k)
+            assert np.array_equal(assoc[t][b, :m], a)
+            assert np.all(assoc[t][b, m:] == -1)
+        assert np.array_equal(known[b], k)
+        worst = max(worst, state_err(states[b], o.state), sigma_err(bt.sigma(b), o.sigma))
+    assert worst < TOL, worst
+
+
+def test_large_map_stream_engine(gpu_pkg):
+    """n = 1,000 landmarks (N = 2,003): the HBM-streamed engine against the O(N^2) oracle, both verbs."""
+    n = 1000
+    tg = gpu_pkg.tracegen
+    w = tg.grid_world(40, 25, pitch=0.45, n_slots=n, max_visible=1.0)
+    tr = tg.simulate_known(w, 1, 12, seed=1)
+    f = gpu_pkg.EKF_SLAM(n)
+    assert f.engine == gpu_pkg.ENGINE_STREAM
+    o = OracleEKF(n)
+    ex, es = _run_known(f, o, tr, check_every=4)
+    assert int(tr["vis"].sum()) > 40
+    assert ex < TOL and es < TOL, (ex, es)
+    # then unknown association on top of the converged map: all landmarks known
+    known_f = np.ones(n, np.uint8)
+    known_o = np.ones(n, np.uint8)
+    tu = tg.simulate_unknown(w, 1, 3, seed=1)
+    for t in range(3):
+        m = int(tu["count"][t, 0])
+        meas = tu["meas"][t, 0, :m]
+        # measurements come from a different trajectory prefix, so most will be gated out: both sides must agree
+        r = f.data_association(meas, known_f)
+        a, dmin, sec, cr = o.data_association(meas, known_o)
+        assert np.array_equal(r["assoc"], a)
+        np.testing.assert_allclose(r["dmin"], dmin, rtol=1e-7, atol=1e-9)
+    assert state_err(f.state, o.state) < TOL and sigma_err(f.sigma, o.sigma) < TOL
+
+
+def test_invalid_arguments_do_not_crash(gpu_pkg):
+    with pytest.raises(gpu_pkg.EkfError):
+        gpu_pkg.EKF_SLAM(0)
+    with pytest.raises(gpu_pkg.EkfError):
+        gpu_pkg.EKF_SLAM(20, device=99)
+    with pytest.raises(gpu_pkg.EkfError):
+        gpu_pkg.EKF_SLAM(200, engine=gpu_pkg.ENGINE_FUSED)
+    f = gpu_pkg.EKF_SLAM(20)
+    with pytest.raises(ValueError):
+        f.measurement(np.zeros(10), np.zeros(20, np.uint8))
+    known = np.zeros(20, np.uint8)
+    f.data_association(np.zeros((0, 2)), known)  # empty measurement list is a no-op
+    assert known.sum() == 0 and f.update_count == 0
