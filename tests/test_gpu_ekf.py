@@ -95,7 +95,11 @@ def _unknown_run(gpu_pkg, n, eng, steps, seed, n_tubes=None):
         res = f.data_association(meas, kf)
         a_o, dmin_o, sec_o, cr_o = o.data_association(meas, ko)
         # a decision is "away from a tie" when neither gate nor the runner-up is within 1e-6 (relative) of dmin
-        margin = np.minimum.reduce([np.abs(dmin_o - 10.0), np.abs(dmin_o - 1.0), np.abs(sec_o - dmin_o)])
+        # (dmin == 10.0 exactly means "no candidate below the gate": then only the runner-up's distance to the
+        # gate matters)
+        has = dmin_o < 10.0
+        margin = np.where(has, np.minimum.reduce([np.abs(dmin_o - 10.0), np.abs(dmin_o - 1.0), np.abs(sec_o - dmin_o)]),
+                          np.abs(sec_o - 10.0))
         clear = margin > 1e-6 * np.maximum(1.0, np.abs(dmin_o))
         n_meas += m
         n_tie += int((~clear).sum())
