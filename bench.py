@@ -1,0 +1,411 @@
+#!/usr/bin/env python
+"""bench.py — EKF measurement-updates/s on synthetic nurtlesim-shaped trajectories (BASELINE.json metric).
+
+Headline workload (config.workload = "cfg3"): a Monte-Carlo batch of 65,536 independent filters x 20 landmark
+slots PER GPU (weak scaling: filters are sharded over ranks with no data-path collective; ranks only
+all-reduce error statistics), one "step" = prediction + measurement() for every filter (nuslam/src/slam.cpp:433-434).
+Also measured at N=1 and reported in the same JSON line: the single large map (cfg4, n = 8,192, Sigma = 2.1 GB)
+whose streamed rank-2 sweep is the clean HBM-roofline kernel.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import ctypes
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "tests")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+METRIC = "ekf_measurement_updates_per_sec"
+UNIT = "updates/s"
+N_SLOTS = 20
+FILTERS_PER_GPU = 65536
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """Samples SM clock and throttle reasons with NVML while the timed region runs."""
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._t = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception as e:  # NVML missing: report that, do not invent numbers
+            self.nv = None
+            self.err = repr(e)
+
+    def _loop(self):
+        nv = self.nv
+        names = {"hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40,
+                 "hw_power_brake_slowdown": 0x80, "sw_power_cap": 0x4}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(
+                    nv, "nvmlDeviceGetCurrentClocksEventReasons") else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(0.001)
+
+    def start(self):
+        if self.nv:
+            self._t = threading.Thread(target=self._loop, daemon=True)
+            self._t.start()
+
+    def stop(self):
+        if self._t:
+            self._stop.set()
+            self._t.join()
+        if not self.nv:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "error": getattr(self, "err", "nvml unavailable")}
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+# ----------------------------------------------------------------------------- CPU legs (oracle/ as the checker)
+def cpu_reference_known(cores, steps_inner, seed=1234, repeats=1):
+    """The reference's own rigid2d::EKF_SLAM (oracle/_ref, built from the reference sources), one filter per host
+    core, on the same kind of traces.  Returns (updates/s, description, kind)."""
+    import _oracle
+    import ekf_slam_ml_b200 as pkg
+    tg = pkg.tracegen
+    tr = tg.simulate_known(tg.dense_world(N_SLOTS), cores, steps_inner, seed=seed)
+    tw = np.ascontiguousarray(tr["twists"].transpose(1, 0, 2))   # [f][t][2]
+    xy = np.ascontiguousarray(tr["xy"].transpose(1, 0, 2))
+    vis = np.ascontiguousarray(tr["vis"].transpose(1, 0, 2))
+    L = _oracle.ref_lib()
+    best = None
+    if L is not None:
+        upd = ctypes.c_int64()
+        for _ in range(repeats):
+            sec = L.ref_bench_known(N_SLOTS, cores, steps_inner, tw.ctypes.data_as(ctypes.POINTER(ctypes.c_double)),
+                                    xy.ctypes.data_as(ctypes.POINTER(ctypes.c_double)),
+                                    vis.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)), ctypes.byref(upd), None)
+            v = upd.value / sec
+            best = v if best is None else max(best, v)
+        return best, f"{cores} filters x {steps_inner} steps (prediction+measurement), n=20, one std::thread per filter; " \
+                     f"reference ekf_slam.cpp compiled -O3 against the Armadillo stand-in over OpenBLAS (1 BLAS thread)", "reference"
+    # no reference build on this box: the plain-C port, one python thread per filter (ctypes releases the GIL)
+    Lo = _oracle.oracle_lib()
+    filters = [_oracle.OracleEKF(N_SLOTS) for _ in range(cores)]
+    counts = [0] * cores
+
+    def run(f):
+        counts[f] = Lo.oracle_run_known(filters[f].h, steps_inner, tw[f].ctypes.data_as(ctypes.POINTER(ctypes.c_double)),
+                                        xy[f].ctypes.data_as(ctypes.POINTER(ctypes.c_double)),
+                                        vis[f].ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)))
+    t0 = time.perf_counter()
+    th = [threading.Thread(target=run, args=(f,)) for f in range(cores)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    sec = time.perf_counter() - t0
+    return sum(counts) / sec, f"{cores} filters x {steps_inner} steps, plain-C O(N^2) port (oracle/ekf_oracle.c)", "port"
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = host_cores()
+    steps_inner = 400
+    vals = []
+    for _ in range(args.warmup):
+        cpu_reference_known(cores, steps_inner)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        v, sample, kind = cpu_reference_known(cores, steps_inner)
+        vals.append(v)
+    wall = time.perf_counter() - t0
+    value = float(np.mean(vals))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * wall / max(1, args.steps), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "cfg3: Monte-Carlo batch of independent filters x 20 landmarks, known association "
+                               "(bounded sample: one filter per host core)", "n_landmarks": N_SLOTS},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------- our arm
+def large_map_leg(pkg, device, n_lm, timed_updates, peak_gbs, want_cpu):
+    """cfg4: one filter, n_lm landmarks; streamed gain + sweep per correction."""
+    tg = pkg.tracegen
+    nx = int(round(np.sqrt(2 * n_lm)))
+    ny = n_lm // nx
+    assert nx * ny == n_lm, "large map expects n = nx*ny with nx = sqrt(2n)"
+    w = tg.grid_world(nx, ny, pitch=0.5, n_slots=n_lm, max_visible=0.7)
+    steps = 64
+    tr = tg.simulate_known(w, 1, steps, seed=99)
+    f = pkg.EKF_SLAM(n_lm, device=device)
+    N = 3 + 2 * n_lm
+    # first call: initialise every landmark (ekf_slam.cpp:113-128), then a few warm-up corrections
+    t = 0
+    done = 0
+    per_update_ms = []
+    l0 = None
+    while t < steps:
+        nvis = int(tr["vis"][t, 0].sum())
+        timed = t >= 3
+        if timed and l0 is None:
+            l0 = f.launch_count
+        if timed and nvis:
+            f.sync()
+            f.timer_start()
+        f.prediction(tuple(tr["twists"][t, 0]))
+        f.measurement(tr["xy"][t, 0], tr["vis"][t, 0])
+        if timed and nvis:
+            ms = f.timer_stop()
+            per_update_ms.append(ms / nvis)
+            done += nvis
+        t += 1
+        if done >= timed_updates:
+            break
+    launches = f.launch_count - (l0 or 0)
+    ms_upd = float(np.mean(per_update_ms))
+    alg_bytes = 16.0 * N * N
+    out = {
+        "workload": f"cfg4: single map, n={n_lm} landmarks (N={N}, Sigma {8.0 * N * N / 1e9:.3f} GB), known association, "
+                    f"prediction + gain + streamed rank-2 sweep per correction",
+        "value": 1e3 / ms_upd, "unit": UNIT, "updates_timed": done, "ms_per_update": ms_upd,
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "achieved": alg_bytes / (ms_upd * 1e-3) / 1e9, "peak": peak_gbs, "unit": "GB/s",
+                     "frac": alg_bytes / (ms_upd * 1e-3) / 1e9 / peak_gbs, "traffic": None,
+                     "kernel": "k_large_sweep (+ k_large_gain, predict; whole-update time used)",
+                     "algorithmic_bytes_per_update": alg_bytes},
+    }
+    if want_cpu:
+        import _oracle
+        o = _oracle.OracleEKF(n_lm)
+        o.prediction(*tr["twists"][0, 0])
+        o.measurement(tr["xy"][0, 0], tr["vis"][0, 0])
+        vis = np.zeros(n_lm, np.uint8)
+        vis[np.flatnonzero(tr["vis"][5, 0])[:3]] = 1
+        t0 = time.perf_counter()
+        o.measurement(tr["xy"][5, 0], vis)
+        sec = time.perf_counter() - t0
+        out["cpu_baseline"] = {"value": float(vis.sum()) / sec, "unit": UNIT, "cores": 1, "kind": "port",
+                               "sample": f"{int(vis.sum())} corrections at N={N}, plain-C O(N^2) port (the dense reference "
+                                         f"needs 2N^3 = {2.0 * N ** 3 / 1e12:.1f} TFLOP per correction and is intractable)"}
+    f.close()
+    return out
+
+
+def run_ours(args):
+    import ekf_slam_ml_b200 as pkg
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist_mod
+        torch.cuda.set_device(local)
+        dist_mod.init_process_group("nccl", device_id=torch.device("cuda", local))
+        dist = dist_mod
+    assert pkg.device_count() > local, "bench.py needs a CUDA device per rank (no CPU fallback)"
+    peak_gbs, peak_src = measured_peaks()
+    tg = pkg.tracegen
+    B, n, K, W = args.filters, N_SLOTS, args.steps, args.warmup
+    N = 3 + 2 * n
+    T = W + K
+    # ---- synthetic traces: filter index = rank*B + b, seeds differ per filter
+    # 1 init-only step + T steps for the device-resident leg + T steps for the end-to-end leg (one continuous run)
+    tr = tg.simulate_known(tg.dense_world(n), B, 2 * T + 1, seed=2026, first_filter=rank * B, workers=host_cores())
+    bt = pkg.EKFBatch(B, n, device=local)
+    # step 0 of the trace is the node's init-only call; run it before anything is timed
+    bt.step_known(np.ascontiguousarray(tr["twists"][0]), np.ascontiguousarray(tr["xy"][0]), np.ascontiguousarray(tr["vis"][0]))
+    bt.sync()
+    tw_h = pkg.PinnedBuffer((T, B, 2), np.float64)
+    xy_h = pkg.PinnedBuffer((T, B, 2 * n), np.float64)
+    vis_h = pkg.PinnedBuffer((T, B, n), np.uint8)
+    tw_h.array[...] = tr["twists"][T + 1:]
+    xy_h.array[...] = tr["xy"][T + 1:]
+    vis_h.array[...] = tr["vis"][T + 1:]
+    poses_h = [pkg.PinnedBuffer((B, 3), np.float64) for _ in range(2)]
+    upd_A = tr["vis"][1:T + 1].reshape(T, -1).sum(axis=1).astype(np.int64)
+    upd_B = tr["vis"][T + 1:].reshape(T, -1).sum(axis=1).astype(np.int64)
+
+    def barrier():
+        if dist:
+            dist.barrier()
+
+    import torch
+    torch.cuda.set_device(local)
+    # ---- leg A (`value`): inputs resident in HBM when the timed region starts
+    d_tw = torch.from_numpy(np.ascontiguousarray(tr["twists"][1:T + 1])).cuda()
+    d_xy = torch.from_numpy(np.ascontiguousarray(tr["xy"][1:T + 1])).cuda()
+    d_vis = torch.from_numpy(np.ascontiguousarray(tr["vis"][1:T + 1])).cuda()
+    torch.cuda.synchronize()
+
+    def dev_step(t):
+        bt.step_known_dev(d_tw[t].data_ptr(), d_xy[t].data_ptr(), d_vis[t].data_ptr())
+
+    for t in range(W):
+        dev_step(t)
+    bt.sync()
+    sampler = ClockSampler(local)
+    barrier()
+    torch.cuda.synchronize()
+    l0 = bt.launch_count
+    sampler.start()
+    bt.timer_start()
+    for t in range(W, T):
+        dev_step(t)
+    total_ms = bt.timer_stop()
+    torch.cuda.synchronize()
+    barrier()
+    clocks = sampler.stop()
+    launches = bt.launch_count - l0
+    # The timed region holds exactly K launches of one kernel on one stream, so the average launch duration of
+    # the dominant kernel is total_ms / K (CUDA events on the launching stream).
+    updates_A = int(upd_A[W:T].sum())
+    kern_ms_avg = total_ms / K
+    upd_launch = float(upd_A[W:T].mean())
+    t_ms = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
+    u_all = torch.tensor([updates_A], dtype=torch.float64, device="cuda")
+    if dist:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(u_all, op=dist.ReduceOp.SUM)
+    total_ms_max = float(t_ms.item())
+    updates_all = float(u_all.item())
+    value = updates_all / (total_ms_max * 1e-3)
+
+    # ---- leg B (`e2e`): host (pinned) buffers through the public verbs; the H2D copy of each step's inputs and the
+    # D2H read of its poses are inside the timed region.  The filters continue the same trajectories.
+    def host_step(t):
+        bt.step_known(tw_h.array[t].ctypes.data, xy_h.array[t].ctypes.data, vis_h.array[t].ctypes.data)
+        bt.poses_async(poses_h[t & 1])
+
+    for t in range(W):
+        host_step(t)
+    bt.sync()
+    barrier()
+    torch.cuda.synchronize()
+    bt.timer_start()
+    for t in range(W, T):
+        host_step(t)
+    e2e_ms = bt.timer_stop()
+    bt.sync()
+    barrier()
+    e_ms = torch.tensor([e2e_ms], dtype=torch.float64, device="cuda")
+    u_b = torch.tensor([float(upd_B[W:T].sum())], dtype=torch.float64, device="cuda")
+    if dist:
+        dist.all_reduce(e_ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(u_b, op=dist.ReduceOp.SUM)
+    e2e_value = float(u_b.item()) / (float(e_ms.item()) * 1e-3)
+    h2d = B * (2 * 8 + 2 * n * 8 + n)
+    d2h = B * 3 * 8
+
+    # ---- error statistics: the only inter-rank exchange of this workload (NCCL all-reduce of 4 doubles)
+    err = bt.pose_error(np.ascontiguousarray(tr["truth"][2 * T][:, [0, 1, 2]]))
+    e_t = torch.tensor(err, dtype=torch.float64, device="cuda")
+    if dist:
+        dist.all_reduce(e_t, op=dist.ReduceOp.SUM)
+    err = e_t.cpu().numpy()
+
+    # ---- roofline of the dominant kernel (ekf_fused_kernel<20>)
+    step_bytes = B * (2.0 * 8 * N * N)                      # Sigma in + out, once per filter and step
+    conv_bytes = 16.0 * N * N * upd_launch                  # 16 N^2 per measurement-update
+    roof = {
+        "bound": "hbm", "kernel": "ekf_fused_kernel<20>", "unit": "GB/s", "peak": peak_gbs, "peak_source": peak_src,
+        "achieved": step_bytes / (kern_ms_avg * 1e-3) / 1e9,
+        "frac": step_bytes / (kern_ms_avg * 1e-3) / 1e9 / peak_gbs,
+        "traffic": None,
+        "algorithmic_bytes_per_launch": step_bytes,
+        "note": "unit = one filter-step (prediction + all of the step's corrections with Sigma resident on chip): "
+                "16 N^2 B = one HBM read + one HBM write of Sigma; per_update_* uses SURVEY.md's 16 N^2 per correction "
+                "and may exceed 1 because the step's corrections share one pass over Sigma",
+        "per_update_achieved": conv_bytes / (kern_ms_avg * 1e-3) / 1e9,
+        "per_update_frac": conv_bytes / (kern_ms_avg * 1e-3) / 1e9 / peak_gbs,
+        "updates_per_launch": upd_launch, "kernel_ms": kern_ms_avg,
+    }
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": total_ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "cfg3: Monte-Carlo batch, 65,536 independent filters x 20 landmark slots per GPU, "
+                               "known association (prediction + measurement per step), nurtlesim-shaped circle trajectories, "
+                               "20-tube world", "filters_per_gpu": B, "n_landmarks": n, "state_dim": N,
+                   "l2": "inputs larger than L2 (Sigma batch = %.0f MB per step)" % (B * 8.0 * N * N / 1e6),
+                   "updates_per_step_per_gpu": upd_launch},
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                "ms_per_step": float(e_ms.item()) / K},
+        "gpu_launches": int(launches),
+        "roofline": roof,
+        "pose_rmse": {"x": float(np.sqrt(err[0] / err[3])), "y": float(np.sqrt(err[1] / err[3])),
+                      "theta": float(np.sqrt(err[2] / err[3])), "filters": int(err[3])},
+    }
+    if rank == 0 and world == 1:
+        cores = host_cores()
+        v, sample, kind = cpu_reference_known(cores, 1500)
+        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample}
+        if not args.skip_large:
+            bt.close()
+            del d_tw, d_xy, d_vis
+            torch.cuda.empty_cache()
+            line["large_map"] = large_map_leg(pkg, local, args.large_n, args.large_updates, peak_gbs, want_cpu=True)
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if dist:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--filters", type=int, default=FILTERS_PER_GPU, help="filters per GPU (cfg3 = 65536)")
+    ap.add_argument("--large-n", type=int, default=8192)
+    ap.add_argument("--large-updates", type=int, default=200)
+    ap.add_argument("--skip-large", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

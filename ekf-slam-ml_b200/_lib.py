@@ -73,6 +73,10 @@ SIGNATURES = {
     "ekf_batch_sync": (ctypes.c_int, [ctypes.c_void_p]),
     "ekf_batch_device_pointers": (ctypes.c_int, [ctypes.c_void_p, c_void_pp, c_i64_p, c_void_pp, c_i64_p]),
     "ekf_batch_stream": (ctypes.c_void_p, [ctypes.c_void_p]),
+    "ekf_timer_start": (ctypes.c_int, [ctypes.c_void_p]),
+    "ekf_timer_stop": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_float)]),
+    "ekf_batch_timer_start": (ctypes.c_int, [ctypes.c_void_p]),
+    "ekf_batch_timer_stop": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_float)]),
     "ekf_batch_launch_count": (ctypes.c_int, [ctypes.c_void_p, c_u64_p]),
     "ekf_normalize_angles": (ctypes.c_int, [c_double_p, c_double_p, ctypes.c_int64, ctypes.c_int]),
     "ekf_body_twist": (ctypes.c_int, [ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_double, c_double_p]),

@@ -183,6 +183,7 @@ struct ekf_filter {
     int* d_known_count = nullptr;
     int assoc_blocks = 0;
     int sm_count = 148;
+    cudaEvent_t t0 = nullptr, t1 = nullptr;
 };
 
 namespace {
@@ -218,6 +219,8 @@ int free_filter(ekf_filter* h) {
         if (h->ring_ev[i]) cudaEventDestroy(h->ring_ev[i]);
     }
     if (h->h_out) cudaFreeHost(h->h_out);
+    if (h->t0) cudaEventDestroy(h->t0);
+    if (h->t1) cudaEventDestroy(h->t1);
     if (h->stream) cudaStreamDestroy(h->stream);
     cudaGetLastError();
     delete h;
@@ -693,6 +696,25 @@ int ekf_launch_count(ekf_filter* h, uint64_t* out) {
     *out = h->launches;
     return EKF_OK;
 }
+// CUDA-event stopwatch on the handle's own stream (torch.cuda.Event only sees torch's streams).
+int ekf_timer_start(ekf_filter* h) {
+    if (!h) return fail(EKF_ERR_INVALID, "null handle");
+    DeviceGuard g(h->device);
+    if (!h->t0) {
+        CU(cudaEventCreate(&h->t0));
+        CU(cudaEventCreate(&h->t1));
+    }
+    CU(cudaEventRecord(h->t0, h->stream));
+    return EKF_OK;
+}
+int ekf_timer_stop(ekf_filter* h, float* ms_out) {
+    if (!h || !ms_out || !h->t0) return fail(EKF_ERR_INVALID, "timer not started");
+    DeviceGuard g(h->device);
+    CU(cudaEventRecord(h->t1, h->stream));
+    CU(cudaEventSynchronize(h->t1));
+    CU(cudaEventElapsedTime(ms_out, h->t0, h->t1));
+    return EKF_OK;
+}
 
 }  // extern "C"
 
@@ -725,6 +747,7 @@ struct ekf_batch {
     double* d_poses = nullptr;
     double* d_acc4 = nullptr;
     double* d_truth = nullptr;
+    cudaEvent_t t0 = nullptr, t1[3] = {nullptr, nullptr, nullptr};
 };
 
 namespace {
@@ -752,6 +775,9 @@ int free_batch(ekf_batch* b) {
     cudaFree(b->d_truth);
     if (b->ev_step) cudaEventDestroy(b->ev_step);
     if (b->ev_out) cudaEventDestroy(b->ev_out);
+    if (b->t0) cudaEventDestroy(b->t0);
+    for (int i = 0; i < 3; ++i)
+        if (b->t1[i]) cudaEventDestroy(b->t1[i]);
     if (b->stream) cudaStreamDestroy(b->stream);
     if (b->copy_stream) cudaStreamDestroy(b->copy_stream);
     if (b->out_stream) cudaStreamDestroy(b->out_stream);
@@ -1032,6 +1058,33 @@ int ekf_batch_device_pointers(ekf_batch* b, void** sigma, int64_t* sigma_stride,
     if (sigma_stride) *sigma_stride = b->sig_stride;
     if (state) *state = b->d_state;
     if (state_stride) *state_stride = b->st_stride;
+    return EKF_OK;
+}
+// Stopwatch over all three of the handle's streams: start is recorded on the (idle) compute stream, stop on
+// compute, copy and output streams; the elapsed time is the latest of the three.
+int ekf_batch_timer_start(ekf_batch* b) {
+    if (!b) return fail(EKF_ERR_INVALID, "null handle");
+    DeviceGuard g(b->device);
+    if (!b->t0) {
+        CU(cudaEventCreate(&b->t0));
+        for (int i = 0; i < 3; ++i) CU(cudaEventCreate(&b->t1[i]));
+    }
+    CU(cudaEventRecord(b->t0, b->stream));
+    return EKF_OK;
+}
+int ekf_batch_timer_stop(ekf_batch* b, float* ms_out) {
+    if (!b || !ms_out || !b->t0) return fail(EKF_ERR_INVALID, "timer not started");
+    DeviceGuard g(b->device);
+    cudaStream_t st[3] = {b->stream, b->copy_stream, b->out_stream};
+    float best = 0.f;
+    for (int i = 0; i < 3; ++i) CU(cudaEventRecord(b->t1[i], st[i]));
+    for (int i = 0; i < 3; ++i) {
+        float ms = 0.f;
+        CU(cudaEventSynchronize(b->t1[i]));
+        CU(cudaEventElapsedTime(&ms, b->t0, b->t1[i]));
+        best = ms > best ? ms : best;
+    }
+    *ms_out = best;
     return EKF_OK;
 }
 int ekf_batch_launch_count(ekf_batch* b, uint64_t* out) {

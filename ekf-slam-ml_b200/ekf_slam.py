@@ -196,6 +196,14 @@ class EKF_SLAM:
     def sync(self):
         check(self._L.ekf_sync(self._h))
 
+    def timer_start(self):
+        check(self._L.ekf_timer_start(self._h))
+
+    def timer_stop(self):
+        ms = ctypes.c_float()
+        check(self._L.ekf_timer_stop(self._h, ctypes.byref(ms)))
+        return ms.value
+
     def clone(self):
         other = object.__new__(EKF_SLAM)
         other._L, other.n, other.N, other.last_assoc = self._L, self.n, self.N, None
@@ -330,6 +338,14 @@ class EKFBatch:
 
     def sync(self):
         check(self._L.ekf_batch_sync(self._h))
+
+    def timer_start(self):
+        check(self._L.ekf_batch_timer_start(self._h))
+
+    def timer_stop(self):
+        ms = ctypes.c_float()
+        check(self._L.ekf_batch_timer_stop(self._h, ctypes.byref(ms)))
+        return ms.value
 
     def device_pointers(self):
         s, st = ctypes.c_void_p(), ctypes.c_void_p()

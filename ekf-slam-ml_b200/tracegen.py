@@ -256,12 +256,25 @@ class TubeWorldSim:
         return (min_r + w.range_std * noise).astype(np.float32)
 
 
-def simulate_known(world: World, B: int, steps: int, seed: int = 0, first_filter: int = 0):
+def _parallel(fn, world, B, steps, seed, first_filter, workers, **kw):
+    """Run `fn` on contiguous filter chunks in threads (filters are independent and the RNG is keyed on the
+    filter index, so the result is identical to a single call) and concatenate along the filter axis."""
+    from concurrent.futures import ThreadPoolExecutor
+    chunk = -(-B // workers)
+    jobs = [(first_filter + s, min(chunk, B - s)) for s in range(0, B, chunk)]
+    with ThreadPoolExecutor(max_workers=workers) as ex:
+        parts = list(ex.map(lambda j: fn(world, j[1], steps, seed, j[0], **kw), jobs))
+    return {k: np.concatenate([p[k] for p in parts], axis=1) for k in parts[0]}
+
+
+def simulate_known(world: World, B: int, steps: int, seed: int = 0, first_filter: int = 0, workers: int = 1):
     """`steps` SLAM steps (one per fake-sensor message) for B filters, known association.
 
     Returns dict of time-major arrays: twists [T,B,2] (dtheta, dx), xy [T,B,2*n_slots],
     vis [T,B,n_slots] uint8 (all zero at step 0: the node's first measurement() call only initialises,
     slam.cpp:315-327), truth [T,B,3] (x, y, theta)."""
+    if workers > 1 and B >= 4 * workers:
+        return _parallel(simulate_known, world, B, steps, seed, first_filter, workers)
     sim = TubeWorldSim(world, B, seed, first_filter)
     n, nt = world.n_slots, min(world.n_tubes, world.n_slots)
     tw = np.zeros((steps, B, 2))

@@ -131,6 +131,12 @@ int ekf_batch_sync(ekf_batch* b);
 int ekf_batch_device_pointers(ekf_batch* b, void** sigma, int64_t* sigma_stride, void** state,
                               int64_t* state_stride);
 void* ekf_batch_stream(ekf_batch* b);
+/* CUDA-event stopwatches on the handles' own streams (for bench.py: torch.cuda.Event sees only torch's
+ * streams).  The batch stop returns the latest completion over its compute, copy and output streams. */
+int ekf_timer_start(ekf_filter* h);
+int ekf_timer_stop(ekf_filter* h, float* ms_out);
+int ekf_batch_timer_start(ekf_batch* b);
+int ekf_batch_timer_stop(ekf_batch* b, float* ms_out);
 /* kernels launched by this handle so far (bench.py's gpu_launches) */
 int ekf_batch_launch_count(ekf_batch* b, uint64_t* out);
 int ekf_launch_count(ekf_filter* h, uint64_t* out);
