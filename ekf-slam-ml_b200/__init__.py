@@ -5,6 +5,7 @@ root-level shim:  ``import ekf_slam_ml_b200``.
 """
 from . import _lib, tracegen
 from ._lib import EkfError, device_count
+from .circle_fitting import CircleFitting
 from .ekf_slam import (EKF_SLAM, ENGINE_AUTO, ENGINE_FUSED, ENGINE_STREAM, EKFBatch, PinnedBuffer, Twist2D,
                        Vector2D, body_twist, normalize_angle)
 

@@ -80,6 +80,23 @@ SIGNATURES = {
     "ekf_batch_launch_count": (ctypes.c_int, [ctypes.c_void_p, c_u64_p]),
     "ekf_normalize_angles": (ctypes.c_int, [c_double_p, c_double_p, ctypes.c_int64, ctypes.c_int]),
     "ekf_body_twist": (ctypes.c_int, [ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_double, c_double_p]),
+    # include/circle_fit_b200.h
+    "circles_last_error": (ctypes.c_char_p, []),
+    "circles_max_clusters": (ctypes.c_int, []),
+    "circles_max_beams": (ctypes.c_int, []),
+    "circles_create": (ctypes.c_int, [ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_void_pp]),
+    "circles_destroy": (ctypes.c_int, [ctypes.c_void_p]),
+    "circles_run_f32": (ctypes.c_int, [ctypes.c_void_p, c_float_p, ctypes.c_int64, c_double_p, c_i32_p]),
+    "circles_run_f64": (ctypes.c_int, [ctypes.c_void_p, c_double_p, ctypes.c_int64, c_double_p, c_i32_p]),
+    "circles_run_dev_f32": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64]),
+    "circles_device_outputs": (ctypes.c_int, [ctypes.c_void_p, c_void_pp, c_void_pp]),
+    "circles_last_clusters": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, c_i32_p, c_i32_p, c_double_p, c_u8_p,
+                                             c_double_p]),
+    "circles_fit_clusters": (ctypes.c_int, [ctypes.c_void_p, c_double_p, c_i32_p, ctypes.c_int, c_double_p, c_u8_p]),
+    "circles_sync": (ctypes.c_int, [ctypes.c_void_p]),
+    "circles_timer_start": (ctypes.c_int, [ctypes.c_void_p]),
+    "circles_timer_stop": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_float)]),
+    "circles_launch_count": (ctypes.c_int, [ctypes.c_void_p, c_u64_p]),
 }
 
 _lib = None
