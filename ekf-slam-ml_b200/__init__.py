@@ -3,11 +3,11 @@
 The directory name carries a hyphen (it mirrors the reference repo's name), so import it through the
 root-level shim:  ``import ekf_slam_ml_b200``.
 """
-from . import _lib, tracegen
+from . import _lib, sharding, tracegen
 from ._lib import EkfError, device_count
 from .circle_fitting import CircleFitting
 from .ekf_slam import (EKF_SLAM, ENGINE_AUTO, ENGINE_FUSED, ENGINE_STREAM, EKFBatch, PinnedBuffer, Twist2D,
                        Vector2D, body_twist, normalize_angle)
 
 __all__ = ["EKF_SLAM", "EKFBatch", "PinnedBuffer", "Twist2D", "Vector2D", "body_twist", "normalize_angle",
-           "EkfError", "device_count", "tracegen", "ENGINE_AUTO", "ENGINE_FUSED", "ENGINE_STREAM"]
+           "EkfError", "device_count", "tracegen", "sharding", "CircleFitting", "ENGINE_AUTO", "ENGINE_FUSED", "ENGINE_STREAM"]

@@ -150,3 +150,19 @@ def test_unsupported_shapes_fail_loudly(gpu_pkg):
     cf = gpu_pkg.CircleFitting()
     with pytest.raises(gpu_pkg.EkfError):
         cf.run_batch(np.ones((1, 1000)))
+
+
+def test_golden_scans_from_reference(gpu_pkg):
+    """tests/golden/circles_scans.npz: centres, counts, cluster sizes and circle flags from the reference itself."""
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "circles_scans.npz"))
+    S = g["ranges"].shape[0]
+    cf = gpu_pkg.CircleFitting(max_scans=S, max_circles=16)
+    centers, counts = cf.run_batch(g["ranges"])
+    assert np.array_equal(counts, g["counts"])
+    for s in range(S):
+        k = int(counts[s])
+        np.testing.assert_allclose(centers[s, :k], g["centers"][s, :k], rtol=0, atol=1e-9)
+        d = cf.last_clusters(s)
+        nc = int((g["cluster_sizes"][s] > 0).sum())
+        assert d["n"] == nc and [len(i) for i in d["ids"]] == list(g["cluster_sizes"][s, :nc])
+        assert list(d["is_circle"]) == list(g["cluster_is_circle"][s, :nc].astype(bool))

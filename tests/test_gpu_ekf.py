@@ -253,3 +253,93 @@ def test_invalid_arguments_do_not_crash(gpu_pkg):
     known = np.zeros(20, np.uint8)
     f.data_association(np.zeros((0, 2)), known)  # empty measurement list is a no-op
     assert known.sum() == 0 and f.update_count == 0
+
+
+# ---------------------------------------------------------------- golden vectors from the reference's own source
+import os as _os
+
+_GOLD = _os.path.join(_os.path.dirname(_os.path.abspath(__file__)), "golden")
+
+
+@pytest.mark.parametrize("engine", ["fused", "stream"])
+def test_golden_known_association(gpu_pkg, engine):
+    """tests/golden/ekf_known_n20.npz: state / Sigma checkpoints and Mahalanobis probes produced by the reference."""
+    g = np.load(_os.path.join(_GOLD, "ekf_known_n20.npz"))
+    f = gpu_pkg.EKF_SLAM(20, engine=gpu_pkg.ENGINE_FUSED if engine == "fused" else gpu_pkg.ENGINE_STREAM)
+    ck = list(g["checkpoints"])
+    worst = 0.0
+    for t in range(g["twists"].shape[0]):
+        f.prediction(tuple(g["twists"][t]))
+        f.measurement(g["xy"][t], g["vis"][t])
+        if t in ck:
+            k = ck.index(t)
+            worst = max(worst, state_err(f.state, g["state"][k]), sigma_err(f.sigma, g["sigma"][k]))
+    assert worst < TOL, worst
+    for p, (px, py) in enumerate(g["maha_probes"]):
+        for i in range(20):
+            want = g["maha"][p, i]
+            assert abs(f.calculate_maha_dis((px, py), i) - want) <= 1e-8 * max(1.0, abs(want))
+
+
+@pytest.mark.parametrize("engine", ["fused", "stream"])
+def test_golden_unknown_association(gpu_pkg, engine):
+    """tests/golden/ekf_unknown_n20.npz: the reference's known_list after every call, state / Sigma checkpoints."""
+    g = np.load(_os.path.join(_GOLD, "ekf_unknown_n20.npz"))
+    f = gpu_pkg.EKF_SLAM(20, engine=gpu_pkg.ENGINE_FUSED if engine == "fused" else gpu_pkg.ENGINE_STREAM)
+    known = np.zeros(20, np.uint8)
+    ck = list(g["checkpoints"])
+    worst = 0.0
+    for t in range(g["twists"].shape[0]):
+        f.prediction(tuple(g["twists"][t]))
+        m = int(g["count"][t])
+        r = f.data_association(g["meas"][t, :m], known)
+        assert np.array_equal(known, g["known"][t])
+        assert np.array_equal(r["assoc"], g["assoc_from_restatement"][t, :m])
+        if t in ck:
+            k = ck.index(t)
+            worst = max(worst, state_err(f.state, g["state"][k]), sigma_err(f.sigma, g["sigma"][k]))
+    assert worst < TOL, worst
+
+
+def test_golden_n100(gpu_pkg):
+    g = np.load(_os.path.join(_GOLD, "ekf_known_n100.npz"))
+    f = gpu_pkg.EKF_SLAM(100)
+    for t in range(g["twists"].shape[0]):
+        f.prediction(tuple(g["twists"][t]))
+        f.measurement(g["xy"][t], g["vis"][t])
+    assert state_err(f.state, g["state"]) < TOL and sigma_err(f.sigma, g["sigma"]) < TOL
+
+
+def test_scan_to_map_pipeline(gpu_pkg):
+    """cfg2 end to end on the GPU: 360-beam scans -> clustering + circle fit -> data_association, against the same
+    pipeline built from the oracles (numpy/LAPACK circle fit feeding the plain-C filter)."""
+    import sys
+    sys.path.insert(0, _os.path.join(_os.path.dirname(_GOLD), "..", "oracle"))
+    import circle_oracle as co
+    tg = gpu_pkg.tracegen
+    T = 40
+    s = tg.simulate_scans(tg.default_world(20), 1, T, seed=8)
+    cf = gpu_pkg.CircleFitting()
+    f = gpu_pkg.EKF_SLAM(20)
+    o = OracleEKF(20)
+    kf, ko = np.zeros(20, np.uint8), np.zeros(20, np.uint8)
+    n_meas = 0
+    for t in range(T):
+        centers, counts = cf.run_batch(s["ranges"][t])
+        k = int(counts[0])
+        c_o, _ = co.approx_circle_positions(s["ranges"][t, 0].astype(np.float64))
+        assert k == len(c_o)
+        np.testing.assert_allclose(centers[0, :k], c_o, atol=1e-9)
+        f.prediction(tuple(s["twists"][t, 0]))
+        o.prediction(*s["twists"][t, 0])
+        if k:
+            r = f.data_association(centers[0, :k], kf)
+            a, dmin, sec, cr = o.data_association(c_o, ko)
+            has = dmin < 10.0
+            margin = np.where(has, np.minimum.reduce([np.abs(dmin - 10.0), np.abs(dmin - 1.0), np.abs(sec - dmin)]),
+                              np.abs(sec - 10.0))
+            assert np.all(margin > 1e-6), "threshold tie in the fixture: pick another seed"
+            assert np.array_equal(r["assoc"], a) and np.array_equal(kf, ko)
+            n_meas += k
+    assert n_meas > 100 and ko.sum() >= 5
+    assert state_err(f.state, o.state) < 1e-8 and sigma_err(f.sigma, o.sigma) < 1e-8
