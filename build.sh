@@ -1,16 +1,27 @@
 #!/usr/bin/env bash
-# Builds the product library IN-TREE for sm_100a (the .so travels to the GPU box with the snapshot).
-#   ekf-slam-ml_b200/libekfslam_b200.so   C ABI of include/ekf_slam_b200.h (+ circle fitting)
+# Builds the product libraries IN-TREE for sm_100a (the .so files travel to the GPU box with the snapshot).
+#   ekf-slam-ml_b200/libekfslam_b200.so          C ABI of include/ekf_slam_b200.h + include/circle_fit_b200.h
+#   ekf-slam-ml_b200/libekfslam_sharded_b200.so  C ABI of include/ekf_sharded_b200.h (row-sharded filter; links NCCL)
 set -euo pipefail
 cd "$(dirname "$0")"
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 SRC=ekf-slam-ml_b200/csrc
-OUT=ekf-slam-ml_b200/libekfslam_b200.so
 FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -Xcompiler -fvisibility=default"
-SOURCES=$(ls $SRC/*.cu)
-newest=$(ls -t $SRC/*.cu $SRC/*.cuh include/*.h build.sh | head -1)
+newest=$(ls -t $SRC/*.cu $SRC/*.cuh $SRC/sharded/*.cu include/*.h build.sh | head -1)
+
+OUT=ekf-slam-ml_b200/libekfslam_b200.so
 if [ -f "$OUT" ] && [ "$OUT" -nt "$newest" ] && [ "${FORCE:-0}" != "1" ]; then
-  echo "up to date: $OUT"; exit 0
+  echo "up to date: $OUT"
+else
+  $NVCC $FLAGS ${EXTRA_NVCC_FLAGS:-} -shared -o $OUT $(ls $SRC/*.cu) -lcudart
+  echo "built $OUT"
 fi
-$NVCC $FLAGS ${EXTRA_NVCC_FLAGS:-} -shared -o $OUT $SOURCES -lcudart
-echo "built $OUT"
+
+OUT2=ekf-slam-ml_b200/libekfslam_sharded_b200.so
+if [ -f "$OUT2" ] && [ "$OUT2" -nt "$newest" ] && [ "${FORCE:-0}" != "1" ]; then
+  echo "up to date: $OUT2"
+else
+  # libnccl.so.2 is resolved at load time: torch's bundled NCCL when torch is already imported, the system one otherwise
+  $NVCC $FLAGS ${EXTRA_NVCC_FLAGS:-} -shared -o $OUT2 $SRC/sharded/sharded.cu -lcudart -lnccl
+  echo "built $OUT2"
+fi

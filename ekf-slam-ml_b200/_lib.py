@@ -99,7 +99,46 @@ SIGNATURES = {
     "circles_launch_count": (ctypes.c_int, [ctypes.c_void_p, c_u64_p]),
 }
 
+# include/ekf_sharded_b200.h (separate library: it links NCCL)
+SHARDED_LIB_PATH = os.path.join(_HERE, "libekfslam_sharded_b200.so")
+SIGNATURES_SHARDED = {
+    "ekf_sharded_last_error": (ctypes.c_char_p, []),
+    "ekf_sharded_unique_id": (ctypes.c_int, [ctypes.c_void_p]),
+    "ekf_sharded_create": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, c_void_pp]),
+    "ekf_sharded_create_local": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int, c_void_pp]),
+    "ekf_sharded_destroy": (ctypes.c_int, [ctypes.c_void_p]),
+    "ekf_sharded_predict": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_double, ctypes.c_double]),
+    "ekf_sharded_measurement": (ctypes.c_int, [ctypes.c_void_p, c_double_p, c_u8_p]),
+    "ekf_sharded_data_association": (ctypes.c_int, [ctypes.c_void_p, c_double_p, ctypes.c_int, c_u8_p, c_i32_p,
+                                                    c_double_p, c_double_p, c_u8_p]),
+    "ekf_sharded_get_state": (ctypes.c_int, [ctypes.c_void_p, c_double_p]),
+    "ekf_sharded_rows": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, c_i64_p, c_i64_p]),
+    "ekf_sharded_get_sigma_rows": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, c_double_p, ctypes.c_int64]),
+    "ekf_sharded_update_count": (ctypes.c_int, [ctypes.c_void_p, c_u64_p]),
+    "ekf_sharded_launch_count": (ctypes.c_int, [ctypes.c_void_p, c_u64_p]),
+    "ekf_sharded_sync": (ctypes.c_int, [ctypes.c_void_p]),
+    "ekf_sharded_timer_start": (ctypes.c_int, [ctypes.c_void_p]),
+    "ekf_sharded_timer_stop": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_float)]),
+}
+
 _lib = None
+_lib_sharded = None
+
+
+def load_sharded():
+    """Load the row-sharded engine's library (once).  Raises if it has not been built or NCCL cannot be resolved."""
+    global _lib_sharded
+    if _lib_sharded is not None:
+        return _lib_sharded
+    if not os.path.exists(SHARDED_LIB_PATH):
+        raise ImportError(f"{SHARDED_LIB_PATH} is missing: run ./build.sh")
+    lib = ctypes.CDLL(SHARDED_LIB_PATH)
+    for name, (res, args) in SIGNATURES_SHARDED.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib_sharded = lib
+    return lib
 
 
 def load():

@@ -304,7 +304,7 @@ __global__ void __launch_bounds__(kSweepThreads)
                   double* __restrict__ state, unsigned long long* __restrict__ n_updates) {
     if (cmd && !cmd->do_update) return;
     if (blockIdx.x == 0 && threadIdx.x == 0) {
-        if (sp->valid) {
+        if (sp && sp->valid) {
             for (int s = 0; s < 5; ++s) state[sp->idx[s]] = sp->v[s];
             sp->valid = 0;
         }

@@ -116,19 +116,21 @@ __device__ __forceinline__ Sym2 inv2x2(double s00, double s01, double s10, doubl
 // Mahalanobis distance of measurement (zr, zphi) to landmark i, from the 5x5 block Sigma[idx, idx]
 // (ekf_slam.cpp:217-276).  The bearing innovation is NOT wrapped (:269).  `sig` may point to shared or
 // global memory; ld is the row stride in doubles.
-__device__ __forceinline__ double maha_distance(const double* __restrict__ sig, int64_t ld, int i, double mx,
-                                                double my, double zr, double zphi, double theta, double x,
-                                                double y) {
+// `robot` points at row 0 of Sigma (rows 0..2 are read from it), `lm` at row 3+2i (rows 3+2i, 4+2i); both with
+// row stride ld.  They are the same matrix on one GPU and two different buffers in the row-sharded engine.
+__device__ __forceinline__ double maha_distance_rows(const double* __restrict__ robot, const double* __restrict__ lm,
+                                                     int64_t ld, int i, double mx, double my, double zr, double zphi,
+                                                     double theta, double x, double y) {
     const Hj h = make_hj(mx, my, theta, x, y);
     const int64_t id[5] = {0, 1, 2, 3 + 2 * (int64_t)i, 4 + 2 * (int64_t)i};
     double wl0[5], wl1[5];
 #pragma unroll
     for (int l = 0; l < 5; ++l) {
-        const double s0 = sig[id[0] * ld + id[l]];
-        const double s1 = sig[id[1] * ld + id[l]];
-        const double s2 = sig[id[2] * ld + id[l]];
-        const double s3 = sig[id[3] * ld + id[l]];
-        const double s4 = sig[id[4] * ld + id[l]];
+        const double s0 = robot[id[l]];
+        const double s1 = robot[ld + id[l]];
+        const double s2 = robot[2 * ld + id[l]];
+        const double s3 = lm[id[l]];
+        const double s4 = lm[ld + id[l]];
         wl0[l] = h_row0(h, s1, s2, s3, s4);
         wl1[l] = h_row1(h, s0, s1, s2, s3, s4);
     }
@@ -142,6 +144,13 @@ __device__ __forceinline__ double maha_distance(const double* __restrict__ sig, 
     const double t0 = __dadd_rn(__dmul_rn(v0, pi.i00), __dmul_rn(v1, pi.i10));
     const double t1 = __dadd_rn(__dmul_rn(v0, pi.i01), __dmul_rn(v1, pi.i11));
     return __dadd_rn(__dmul_rn(t0, v0), __dmul_rn(t1, v1));
+}
+
+// Whole Sigma in one buffer (shared memory in the fused engine, global memory in the streamed one).
+__device__ __forceinline__ double maha_distance(const double* __restrict__ sig, int64_t ld, int i, double mx,
+                                                double my, double zr, double zphi, double theta, double x,
+                                                double y) {
+    return maha_distance_rows(sig, sig + (3 + 2 * (int64_t)i) * ld, ld, i, mx, my, zr, zphi, theta, x, y);
 }
 
 // Motion model increments and Jacobian entries (ekf_slam.cpp:67-96): state[0..2] += u, A(1,0)=a1, A(2,0)=a2.

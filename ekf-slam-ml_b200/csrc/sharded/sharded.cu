@@ -1,0 +1,856 @@
+// Engine 3: one filter, covariance row-block-sharded over `world` GPUs (include/ekf_sharded_b200.h).
+// The O(N^2) sweep and the O(N) gathers run on each rank's own rows; per correction the ranks exchange W (all-reduce
+// of the row owners' partial products) and K (all-gather of row slices) with NCCL over NVLink.  A single-process
+// "local" mode keeps `world` shards on one device and replaces the NCCL calls by device copies, so that the sharding
+// arithmetic can be parity-tested on one GPU.
+// Restates rigid2d/src/ekf_slam.cpp:55-106, 108-197, 200-214, 217-276, 278-402.
+#include <cuda_runtime.h>
+#include <nccl.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "../../../include/ekf_sharded_b200.h"
+#include "../ekf_large.cuh"
+
+using namespace ekf;
+
+namespace {
+
+thread_local char g_err[512] = "";
+int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+#define CU(expr)                                                                               \
+    do {                                                                                       \
+        cudaError_t e_ = (expr);                                                               \
+        if (e_ != cudaSuccess) {                                                               \
+            cudaGetLastError();                                                                \
+            return fail((int)e_, "%s failed: %s (line %d)", #expr, cudaGetErrorString(e_), __LINE__); \
+        }                                                                                      \
+    } while (0)
+#define NC(expr)                                                                               \
+    do {                                                                                       \
+        ncclResult_t r_ = (expr);                                                              \
+        if (r_ != ncclSuccess) return fail(1000 + (int)r_, "%s failed: %s (line %d)", #expr, ncclGetErrorString(r_), __LINE__); \
+    } while (0)
+
+// per-correction scalars, replicated on every shard
+struct Ctx {
+    Hj h;
+    Sym2 si;
+    double nu0, nu1, zr, zphi;
+    int i3, active;
+};
+
+// ---- prediction
+__global__ void k_sh_motion(double* __restrict__ state, double* __restrict__ sig_robot, long long ld, double dtheta,
+                            double dx, double* __restrict__ motion_out) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const Motion m = motion_model(state[0], dtheta, dx);
+    if (sig_robot) {  // the rank that owns rows 0..2 also owns the 3x3 robot block
+        double s[3][3];
+        for (int r = 0; r < 3; ++r)
+            for (int c = 0; c < 3; ++c) s[r][c] = sig_robot[r * ld + c];
+        for (int c = 0; c < 3; ++c) {
+            s[1][c] = fma(m.a1, s[0][c], s[1][c]);
+            s[2][c] = fma(m.a2, s[0][c], s[2][c]);
+        }
+        for (int r = 0; r < 3; ++r) {
+            s[r][1] = fma(s[r][0], m.a1, s[r][1]);
+            s[r][2] = fma(s[r][0], m.a2, s[r][2]);
+        }
+        s[0][0] += kQ;
+        s[1][1] += kQ;
+        s[2][2] += kQ;
+        for (int r = 0; r < 3; ++r)
+            for (int c = 0; c < 3; ++c) sig_robot[r * ld + c] = s[r][c];
+    }
+    state[0] = state[0] + m.u0;
+    state[1] = state[1] + m.u1;
+    state[2] = state[2] + m.u2;
+    motion_out[0] = m.a1;
+    motion_out[1] = m.a2;
+}
+__global__ void k_sh_predict_rows12(double* __restrict__ sig, long long ld, int N, const double* __restrict__ motion) {
+    const int k = 3 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= N) return;
+    const double r0 = sig[k];
+    sig[ld + k] = fma(motion[0], r0, sig[ld + k]);
+    sig[2 * ld + k] = fma(motion[1], r0, sig[2 * ld + k]);
+}
+// local rows [lr_begin, rows): columns 1,2 += a * column 0
+__global__ void k_sh_predict_cols(double* __restrict__ sig_local, long long ld, int lr_begin, int rows,
+                                  const double* __restrict__ motion) {
+    const int lr = lr_begin + blockIdx.x * blockDim.x + threadIdx.x;
+    if (lr >= rows) return;
+    double* row = sig_local + (long long)lr * ld;
+    const double c0 = row[0];
+    row[1] = fma(c0, motion[0], row[1]);
+    row[2] = fma(c0, motion[1], row[2]);
+}
+
+// ---- correction
+__global__ void k_sh_ctx_h(const double* __restrict__ state, const double* __restrict__ pose_src,
+                           const UpdateCmd* __restrict__ cmd, int lm_arg, double sx_arg, double sy_arg,
+                           Ctx* __restrict__ ctx) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    int lm = lm_arg, active = 1;
+    double sx = sx_arg, sy = sy_arg;
+    if (cmd) {
+        active = cmd->do_update;
+        lm = cmd->lm;
+        sx = cmd->sx;
+        sy = cmd->sy;
+    }
+    ctx->active = active;
+    if (!active) return;
+    const int i3 = 3 + 2 * lm;
+    ctx->i3 = i3;
+    ctx->h = make_hj(state[i3], state[i3 + 1], pose_src[0], pose_src[1], pose_src[2]);
+    double zr, zphi;
+    range_bearing(sx, sy, zr, zphi);
+    ctx->zr = zr;
+    ctx->zphi = zphi;
+}
+
+// partial W = Hj * Sigma restricted to the rows this shard owns (zeros stand in for the others)
+__global__ void __launch_bounds__(256)
+    k_sh_wpart(const double* __restrict__ sig_local, long long ld, long long r0, long long r1, int N,
+               const Ctx* __restrict__ ctx, double2* __restrict__ Wpart) {
+    const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= ld) return;
+    if (!ctx->active) return;
+    double2 w = make_double2(0.0, 0.0);
+    if (c < N) {
+        const long long id[5] = {0, 1, 2, ctx->i3, ctx->i3 + 1};
+        double s[5];
+#pragma unroll
+        for (int k = 0; k < 5; ++k) s[k] = (id[k] >= r0 && id[k] < r1) ? sig_local[(id[k] - r0) * ld + c] : 0.0;
+        const Hj h = ctx->h;
+        w = make_double2(h_row0(h, s[1], s[2], s[3], s[4]), h_row1(h, s[0], s[1], s[2], s[3], s[4]));
+    }
+    Wpart[c] = w;
+}
+
+__global__ void k_sh_ctx_s(const double2* __restrict__ W2, Ctx* __restrict__ ctx) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    if (!ctx->active) return;
+    const Hj h = ctx->h;
+    const int i3 = ctx->i3;
+    const double2 w0 = W2[0], w1 = W2[1], w2 = W2[2], w3 = W2[i3], w4 = W2[i3 + 1];
+    const double s00 = h_row0(h, w1.x, w2.x, w3.x, w4.x) + kR;
+    const double s01 = h_row1(h, w0.x, w1.x, w2.x, w3.x, w4.x);
+    const double s10 = h_row0(h, w1.y, w2.y, w3.y, w4.y);
+    const double s11 = h_row1(h, w0.y, w1.y, w2.y, w3.y, w4.y) + kR;
+    ctx->si = inv2x2(s00, s01, s10, s11);
+    ctx->nu0 = __dsub_rn(ctx->zr, h.zr);
+    ctx->nu1 = normalize_angle(__dsub_rn(ctx->zphi, h.zphi));
+}
+
+// K rows of this shard: K[r] = (Sigma[r, idx] Hj^T) S^-1
+__global__ void __launch_bounds__(256)
+    k_sh_gain(const double* __restrict__ sig_local, long long ld, long long r0, int rows, const Ctx* __restrict__ ctx,
+              double2* __restrict__ K2) {
+    const int lr = blockIdx.x * blockDim.x + threadIdx.x;
+    if (lr >= rows) return;
+    if (!ctx->active) return;
+    const Hj h = ctx->h;
+    const Sym2 si = ctx->si;
+    const int i3 = ctx->i3;
+    const double* row = sig_local + (long long)lr * ld;
+    const double q0 = row[0], q1 = row[1], q2 = row[2], q3 = row[i3], q4 = row[i3 + 1];
+    const double p0 = h_row0(h, q1, q2, q3, q4), p1 = h_row1(h, q0, q1, q2, q3, q4);
+    K2[r0 + lr] = make_double2(fma(p1, si.i10, p0 * si.i00), fma(p1, si.i11, p0 * si.i01));
+}
+
+// every replica applies the same state update from the gathered K
+__global__ void __launch_bounds__(256)
+    k_sh_state(double* __restrict__ state, const double2* __restrict__ K2, const Ctx* __restrict__ ctx, int N) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= N) return;
+    if (!ctx->active) return;
+    const double2 k = K2[r];
+    double ns = state[r] + fma(k.y, ctx->nu1, k.x * ctx->nu0);
+    if (r == 0) ns = normalize_angle(ns);
+    state[r] = ns;
+}
+
+// ---- association
+__global__ void __launch_bounds__(256)
+    k_sh_assoc_local(const double* __restrict__ robot, const double* __restrict__ sig_local, long long ld, long long r0,
+                     int L0, int L1, const double* __restrict__ state, const double* __restrict__ meas, int j,
+                     const int* __restrict__ known_count_p, AssocPartial* __restrict__ block_partials,
+                     unsigned int* __restrict__ done_counter, AssocPartial* __restrict__ out) {
+    __shared__ AssocPartial shp[8];
+    __shared__ bool is_last;
+    const int known_count = *known_count_p;
+    const int hi = L1 < known_count ? L1 : known_count;
+    double zr, zphi;
+    range_bearing(meas[2 * j], meas[2 * j + 1], zr, zphi);
+    const double theta = state[0], x = state[1], y = state[2];
+    double best = INFINITY, second = INFINITY;
+    int best_i = 0x7fffffff;
+    for (int i = L0 + blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += gridDim.x * blockDim.x) {
+        const double* lm = sig_local + ((3 + 2 * (long long)i) - r0) * ld;
+        double d = maha_distance_rows(robot, lm, ld, i, state[3 + 2 * i], state[4 + 2 * i], zr, zphi, theta, x, y);
+        if (!(d == d)) d = INFINITY;
+        if (d < best) {
+            second = best;
+            best = d;
+            best_i = i;
+        } else if (d < second) {
+            second = d;
+        }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        const double ob = __shfl_xor_sync(0xffffffffu, best, off);
+        const double os = __shfl_xor_sync(0xffffffffu, second, off);
+        const int oi = __shfl_xor_sync(0xffffffffu, best_i, off);
+        assoc_merge(best, second, best_i, ob, os, oi);
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) shp[warp] = AssocPartial{best, second, best_i, 0};
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w) assoc_merge(best, second, best_i, shp[w].best, shp[w].second, shp[w].best_i);
+        block_partials[blockIdx.x] = AssocPartial{best, second, best_i, 0};
+        __threadfence();
+        is_last = (atomicAdd(done_counter, 1u) == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!is_last || threadIdx.x != 0) return;
+    __threadfence();
+    best = INFINITY;
+    second = INFINITY;
+    best_i = 0x7fffffff;
+    for (unsigned int b = 0; b < gridDim.x; ++b) {
+        const volatile AssocPartial* pp = block_partials + b;
+        assoc_merge(best, second, best_i, pp->best, pp->second, pp->best_i);
+    }
+    *done_counter = 0;
+    *out = AssocPartial{best, second, best_i, 0};
+}
+
+// identical on every replica: merge the per-rank partials in rank order and take the decision (ekf_slam.cpp:293-330)
+__global__ void k_sh_decide(const AssocPartial* __restrict__ parts, int world, double* __restrict__ state, int n,
+                            const double* __restrict__ meas, int j, int* __restrict__ known_count_p,
+                            UpdateCmd* __restrict__ cmd, int32_t* __restrict__ assoc_out, double* __restrict__ dmin_out,
+                            double* __restrict__ second_out, uint8_t* __restrict__ created_out) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    double best = INFINITY, second = INFINITY;
+    int best_i = 0x7fffffff;
+    for (int g = 0; g < world; ++g) assoc_merge(best, second, best_i, parts[g].best, parts[g].second, parts[g].best_i);
+    const int known_count = *known_count_p;
+    const double sx = meas[2 * j], sy = meas[2 * j + 1];
+    double min_d = kGateNew;
+    int min_idx = known_count;
+    if (best < kGateNew) {
+        min_d = best;
+        min_idx = best_i;
+        second = fmin(second, kGateNew);
+    } else {
+        second = best;
+    }
+    dmin_out[j] = min_d;
+    second_out[j] = second;
+    int created = 0;
+    if (min_idx == known_count && min_idx < n) {
+        double mx, my;
+        landmark_from_reading(sx, sy, state[0], state[1], state[2], mx, my);
+        state[3 + 2 * min_idx] = mx;
+        state[4 + 2 * min_idx] = my;
+        *known_count_p = known_count + 1;
+        min_d = 0.0;
+        created = 1;
+    }
+    const int upd = min_d < kGateUpdate;
+    cmd->do_update = upd;
+    cmd->lm = min_idx;
+    cmd->created = created;
+    cmd->sx = sx;
+    cmd->sy = sy;
+    assoc_out[j] = upd ? min_idx : -1;
+    created_out[j] = (uint8_t)created;
+}
+
+// local-mode stand-in for the all-reduce of W: dst = sum over shards (rank order)
+__global__ void k_sum_shards(double2* __restrict__ dst, const double2* const* __restrict__ srcs, int world, long long ld) {
+    const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= ld) return;
+    double2 acc = srcs[0][c];
+    for (int g = 1; g < world; ++g) {
+        acc.x += srcs[g][c].x;
+        acc.y += srcs[g][c].y;
+    }
+    dst[c] = acc;
+}
+
+struct Shard {
+    int rank = 0;
+    int L0 = 0, L1 = 0;
+    long long r0 = 0, r1 = 0;
+    int rows = 0;
+    double* sig = nullptr;
+    double* state = nullptr;
+    double2 *K2 = nullptr, *W2 = nullptr, *Wpart = nullptr;
+    double* robot = nullptr;  // 3 x ld; aliases sig on the rank that owns rows 0..2
+    bool robot_owned = false;
+    double *pose0 = nullptr, *motion = nullptr, *meas = nullptr, *xy = nullptr;
+    Ctx* ctx = nullptr;
+    UpdateCmd* cmd = nullptr;
+    AssocPartial *blk = nullptr, *part = nullptr, *parts = nullptr;
+    unsigned int* done = nullptr;
+    int* known_count = nullptr;
+    int32_t* init_flag = nullptr;
+    unsigned long long* nupd = nullptr;
+    int32_t* d_assoc = nullptr;
+    double *d_dmin = nullptr, *d_second = nullptr;
+    uint8_t* d_created = nullptr;
+    int assoc_blocks = 1;
+};
+
+}  // namespace
+
+struct ekf_sharded {
+    int n = 0, N = 0, world = 1, device = 0, sm_count = 148;
+    bool local = false;
+    long long ld = 0;
+    std::vector<Shard> sh;  // NCCL mode: exactly this rank's shard; local mode: all of them
+    std::vector<long long> r0_of, r1_of;
+    ncclComm_t comm = nullptr;
+    cudaStream_t stream = nullptr;
+    int init_flag_host = 0;
+    int m_cap = 0;
+    const double2** d_srcs = nullptr;  // local mode: device array of Wpart pointers
+    uint64_t launches = 0;
+    cudaEvent_t t0 = nullptr, t1 = nullptr;
+    unsigned char* h_stage = nullptr;  // pinned
+    size_t h_stage_bytes = 0;
+};
+
+namespace {
+
+struct Dev {
+    int prev = -1;
+    explicit Dev(int d) {
+        cudaGetDevice(&prev);
+        if (prev != d) cudaSetDevice(d);
+    }
+    ~Dev() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+void partition(ekf_sharded* h) {
+    const int per = (h->n + h->world - 1) / h->world;
+    h->r0_of.resize(h->world);
+    h->r1_of.resize(h->world);
+    for (int g = 0; g < h->world; ++g) {
+        const int L0 = std::min(h->n, g * per), L1 = std::min(h->n, (g + 1) * per);
+        h->r0_of[g] = g == 0 ? 0 : 3 + 2LL * L0;
+        h->r1_of[g] = 3 + 2LL * L1;
+    }
+}
+
+int alloc_shard(ekf_sharded* h, Shard& s, int rank) {
+    const int per = (h->n + h->world - 1) / h->world;
+    s.rank = rank;
+    s.L0 = std::min(h->n, rank * per);
+    s.L1 = std::min(h->n, (rank + 1) * per);
+    s.r0 = h->r0_of[rank];
+    s.r1 = h->r1_of[rank];
+    s.rows = (int)(s.r1 - s.r0);
+    const size_t ld = (size_t)h->ld;
+    CU(cudaMalloc(&s.sig, sizeof(double) * std::max<size_t>(1, (size_t)s.rows) * ld));
+    CU(cudaMalloc(&s.state, sizeof(double) * ld));
+    CU(cudaMalloc(&s.K2, sizeof(double2) * ld));
+    CU(cudaMalloc(&s.W2, sizeof(double2) * ld));
+    CU(cudaMalloc(&s.Wpart, sizeof(double2) * ld));
+    if (rank == 0) {
+        s.robot = s.sig;
+    } else {
+        CU(cudaMalloc(&s.robot, sizeof(double) * 3 * ld));
+        s.robot_owned = true;
+    }
+    CU(cudaMalloc(&s.pose0, 3 * sizeof(double)));
+    CU(cudaMalloc(&s.motion, 2 * sizeof(double)));
+    CU(cudaMalloc(&s.xy, sizeof(double) * 2 * h->n));
+    CU(cudaMalloc(&s.ctx, sizeof(Ctx)));
+    CU(cudaMalloc(&s.cmd, sizeof(UpdateCmd)));
+    s.assoc_blocks = std::max(1, std::min((s.L1 - s.L0 + 255) / 256, 1024));
+    CU(cudaMalloc(&s.blk, sizeof(AssocPartial) * s.assoc_blocks));
+    CU(cudaMalloc(&s.part, sizeof(AssocPartial)));
+    CU(cudaMalloc(&s.parts, sizeof(AssocPartial) * h->world));
+    CU(cudaMalloc(&s.done, sizeof(unsigned int)));
+    CU(cudaMalloc(&s.known_count, sizeof(int)));
+    CU(cudaMalloc(&s.init_flag, sizeof(int32_t)));
+    CU(cudaMalloc(&s.nupd, sizeof(unsigned long long)));
+    CU(cudaMemsetAsync(s.sig, 0, sizeof(double) * std::max<size_t>(1, (size_t)s.rows) * ld, h->stream));
+    CU(cudaMemsetAsync(s.state, 0, sizeof(double) * ld, h->stream));
+    CU(cudaMemsetAsync(s.K2, 0, sizeof(double2) * ld, h->stream));
+    CU(cudaMemsetAsync(s.W2, 0, sizeof(double2) * ld, h->stream));
+    CU(cudaMemsetAsync(s.Wpart, 0, sizeof(double2) * ld, h->stream));
+    CU(cudaMemsetAsync(s.ctx, 0, sizeof(Ctx), h->stream));
+    CU(cudaMemsetAsync(s.cmd, 0, sizeof(UpdateCmd), h->stream));
+    CU(cudaMemsetAsync(s.done, 0, sizeof(unsigned int), h->stream));
+    CU(cudaMemsetAsync(s.known_count, 0, sizeof(int), h->stream));
+    CU(cudaMemsetAsync(s.init_flag, 0, sizeof(int32_t), h->stream));
+    CU(cudaMemsetAsync(s.nupd, 0, sizeof(unsigned long long), h->stream));
+    return 0;  // Sigma0's landmark diagonal (ekf_slam.cpp:29-36) is written by finish_create()
+}
+
+__global__ void k_sh_init_sigma(double* __restrict__ sig_local, long long ld, long long r0, int rows) {
+    const int lr = blockIdx.x * blockDim.x + threadIdx.x;
+    if (lr >= rows) return;
+    const long long r = r0 + lr;
+    if (r >= 3) sig_local[(long long)lr * ld + r] = kSigma0;
+}
+
+int ensure_m(ekf_sharded* h, int m) {
+    if (m <= h->m_cap) return 0;
+    const int cap = std::max(m, 64);
+    CU(cudaStreamSynchronize(h->stream));
+    for (auto& s : h->sh) {
+        cudaFree(s.meas);
+        cudaFree(s.d_assoc);
+        cudaFree(s.d_dmin);
+        cudaFree(s.d_second);
+        cudaFree(s.d_created);
+        CU(cudaMalloc(&s.meas, sizeof(double) * 2 * cap));
+        CU(cudaMalloc(&s.d_assoc, sizeof(int32_t) * cap));
+        CU(cudaMalloc(&s.d_dmin, sizeof(double) * cap));
+        CU(cudaMalloc(&s.d_second, sizeof(double) * cap));
+        CU(cudaMalloc(&s.d_created, cap));
+    }
+    const size_t need = (size_t)cap * 64 + (size_t)h->n * 17 + 256;
+    if (need > h->h_stage_bytes) {
+        if (h->h_stage) cudaFreeHost(h->h_stage);
+        h->h_stage = nullptr;
+        CU(cudaMallocHost((void**)&h->h_stage, need));
+        h->h_stage_bytes = need;
+    }
+    h->m_cap = cap;
+    return 0;
+}
+
+// ---- the three exchanges
+int exchange_W(ekf_sharded* h) {
+    if (h->local) {
+        const int g = (int)((h->ld + 255) / 256);
+        for (auto& s : h->sh) {
+            k_sum_shards<<<g, 256, 0, h->stream>>>(s.W2, h->d_srcs, h->world, h->ld);
+            h->launches++;
+        }
+        CU(cudaGetLastError());
+    } else {
+        Shard& s = h->sh[0];
+        NC(ncclAllReduce(s.Wpart, s.W2, 2 * (size_t)h->ld, ncclDouble, ncclSum, h->comm, h->stream));
+    }
+    return 0;
+}
+int exchange_K(ekf_sharded* h) {
+    if (h->local) {
+        for (auto& src : h->sh)
+            for (auto& dst : h->sh)
+                if (&src != &dst && src.rows > 0)
+                    CU(cudaMemcpyAsync(dst.K2 + src.r0, src.K2 + src.r0, sizeof(double2) * src.rows, cudaMemcpyDeviceToDevice,
+                                       h->stream));
+    } else {
+        Shard& s = h->sh[0];
+        NC(ncclGroupStart());
+        for (int g = 0; g < h->world; ++g) {
+            const long long r0 = h->r0_of[g], rows = h->r1_of[g] - r0;
+            if (rows > 0) NC(ncclBroadcast(s.K2 + r0, s.K2 + r0, 2 * (size_t)rows, ncclDouble, g, h->comm, h->stream));
+        }
+        NC(ncclGroupEnd());
+    }
+    return 0;
+}
+int exchange_robot_rows(ekf_sharded* h) {
+    if (h->local) {
+        for (size_t g = 1; g < h->sh.size(); ++g)
+            CU(cudaMemcpyAsync(h->sh[g].robot, h->sh[0].sig, sizeof(double) * 3 * h->ld, cudaMemcpyDeviceToDevice, h->stream));
+    } else {
+        Shard& s = h->sh[0];
+        NC(ncclBroadcast(s.robot, s.robot, 3 * (size_t)h->ld, ncclDouble, 0, h->comm, h->stream));
+    }
+    return 0;
+}
+int exchange_partials(ekf_sharded* h) {
+    if (h->local) {
+        for (auto& src : h->sh)
+            for (auto& dst : h->sh)
+                CU(cudaMemcpyAsync(dst.parts + src.rank, src.part, sizeof(AssocPartial), cudaMemcpyDeviceToDevice, h->stream));
+    } else {
+        Shard& s = h->sh[0];
+        NC(ncclAllGather(s.part, s.parts, sizeof(AssocPartial), ncclChar, h->comm, h->stream));
+    }
+    return 0;
+}
+
+int sweep_grid(const ekf_sharded* h, const Shard& s) {
+    const long long chunks = (h->ld + kSweepChunk - 1) / kSweepChunk;
+    const long long row_blocks = (s.rows + kSweepRows - 1) / kSweepRows;
+    return (int)std::max(1LL, std::min(chunks * row_blocks, (long long)h->sm_count * 8));
+}
+
+// one landmark correction across all shards
+int correct(ekf_sharded* h, bool use_cmd, bool stale_pose, int lm, double sx, double sy) {
+    const int gl = (int)((h->ld + 255) / 256);
+    for (auto& s : h->sh) {
+        k_sh_ctx_h<<<1, 32, 0, h->stream>>>(s.state, stale_pose ? s.pose0 : s.state, use_cmd ? s.cmd : nullptr, lm, sx, sy, s.ctx);
+        k_sh_wpart<<<gl, 256, 0, h->stream>>>(s.sig, h->ld, s.r0, s.r1, h->N, s.ctx, s.Wpart);
+        h->launches += 2;
+    }
+    CU(cudaGetLastError());
+    int rc = exchange_W(h);
+    if (rc) return rc;
+    for (auto& s : h->sh) {
+        k_sh_ctx_s<<<1, 32, 0, h->stream>>>(s.W2, s.ctx);
+        if (s.rows > 0) k_sh_gain<<<(s.rows + 255) / 256, 256, 0, h->stream>>>(s.sig, h->ld, s.r0, s.rows, s.ctx, s.K2);
+        h->launches += 2;
+    }
+    CU(cudaGetLastError());
+    rc = exchange_K(h);
+    if (rc) return rc;
+    for (auto& s : h->sh) {
+        k_sh_state<<<(h->N + 255) / 256, 256, 0, h->stream>>>(s.state, s.K2, s.ctx, h->N);
+        if (s.rows > 0)
+            k_large_sweep<<<sweep_grid(h, s), kSweepThreads, 0, h->stream>>>(s.sig, h->ld, s.rows, s.K2 + s.r0, s.W2,
+                                                                            use_cmd ? s.cmd : nullptr, nullptr, nullptr, s.nupd);
+        h->launches += 2;
+    }
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int finish_create(ekf_sharded* h) {
+    for (auto& s : h->sh)
+        if (s.rows > 0) {
+            k_sh_init_sigma<<<(s.rows + 255) / 256, 256, 0, h->stream>>>(s.sig, h->ld, s.r0, s.rows);
+            h->launches++;
+        }
+    CU(cudaGetLastError());
+    if (h->local) {
+        std::vector<const double2*> ptrs;
+        for (auto& s : h->sh) ptrs.push_back(s.Wpart);
+        CU(cudaMalloc((void**)&h->d_srcs, sizeof(double2*) * ptrs.size()));
+        CU(cudaMemcpyAsync((void*)h->d_srcs, ptrs.data(), sizeof(double2*) * ptrs.size(), cudaMemcpyHostToDevice, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+    }
+    int rc = ensure_m(h, 64);
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int create_common(int n, int world, int device, ekf_sharded** out, ekf_sharded** hp) {
+    if (!out) return fail(-1, "null out pointer");
+    *out = nullptr;
+    if (n <= 0 || world <= 0 || n < world) return fail(-1, "invalid shape: n=%d world=%d", n, world);
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail((int)e, "cudaGetDeviceCount: %s", cudaGetErrorString(e));
+    }
+    if (device < 0 || device >= count) return fail(-1, "device %d not available (%d visible)", device, count);
+    ekf_sharded* h = new (std::nothrow) ekf_sharded();
+    if (!h) return fail(-3, "out of host memory");
+    h->n = n;
+    h->N = 3 + 2 * n;
+    h->world = world;
+    h->device = device;
+    h->ld = (h->N + 15) & ~15LL;
+    cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device);
+    partition(h);
+    *hp = h;
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* ekf_sharded_last_error(void) { return g_err; }
+
+int ekf_sharded_unique_id(void* id128) {
+    if (!id128) return fail(-1, "null argument");
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is expected to be 128 bytes");
+    ncclUniqueId id;
+    NC(ncclGetUniqueId(&id));
+    memcpy(id128, &id, sizeof(id));
+    return 0;
+}
+
+int ekf_sharded_destroy(ekf_sharded* h) {
+    if (!h) return 0;
+    Dev g(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    for (auto& s : h->sh) {
+        cudaFree(s.sig);
+        cudaFree(s.state);
+        cudaFree(s.K2);
+        cudaFree(s.W2);
+        cudaFree(s.Wpart);
+        if (s.robot_owned) cudaFree(s.robot);
+        cudaFree(s.pose0);
+        cudaFree(s.motion);
+        cudaFree(s.meas);
+        cudaFree(s.xy);
+        cudaFree(s.ctx);
+        cudaFree(s.cmd);
+        cudaFree(s.blk);
+        cudaFree(s.part);
+        cudaFree(s.parts);
+        cudaFree(s.done);
+        cudaFree(s.known_count);
+        cudaFree(s.init_flag);
+        cudaFree(s.nupd);
+        cudaFree(s.d_assoc);
+        cudaFree(s.d_dmin);
+        cudaFree(s.d_second);
+        cudaFree(s.d_created);
+    }
+    if (h->d_srcs) cudaFree((void*)h->d_srcs);
+    if (h->h_stage) cudaFreeHost(h->h_stage);
+    if (h->comm) ncclCommDestroy(h->comm);
+    if (h->t0) cudaEventDestroy(h->t0);
+    if (h->t1) cudaEventDestroy(h->t1);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    cudaGetLastError();
+    delete h;
+    return 0;
+}
+
+int ekf_sharded_create(int n, int rank, int world, const void* id128, int device, ekf_sharded** out) {
+    if (!id128 || rank < 0 || rank >= world) return fail(-1, "invalid rank / id");
+    ekf_sharded* h = nullptr;
+    int rc = create_common(n, world, device, out, &h);
+    if (rc) return rc;
+    Dev g(device);
+    cudaError_t e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) {
+        ekf_sharded_destroy(h);
+        return fail((int)e, "stream: %s", cudaGetErrorString(e));
+    }
+    ncclUniqueId id;
+    memcpy(&id, id128, sizeof(id));
+    ncclResult_t r = ncclCommInitRank(&h->comm, world, id, rank);
+    if (r != ncclSuccess) {
+        h->comm = nullptr;
+        ekf_sharded_destroy(h);
+        return fail(1000 + (int)r, "ncclCommInitRank: %s", ncclGetErrorString(r));
+    }
+    h->sh.resize(1);
+    rc = alloc_shard(h, h->sh[0], rank);
+    if (!rc) rc = finish_create(h);
+    if (rc) {
+        ekf_sharded_destroy(h);
+        return rc;
+    }
+    *out = h;
+    return 0;
+}
+
+int ekf_sharded_create_local(int n, int world, int device, ekf_sharded** out) {
+    ekf_sharded* h = nullptr;
+    int rc = create_common(n, world, device, out, &h);
+    if (rc) return rc;
+    Dev g(device);
+    h->local = true;
+    cudaError_t e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) {
+        ekf_sharded_destroy(h);
+        return fail((int)e, "stream: %s", cudaGetErrorString(e));
+    }
+    h->sh.resize(world);
+    for (int r = 0; r < world && !rc; ++r) rc = alloc_shard(h, h->sh[r], r);
+    if (!rc) rc = finish_create(h);
+    if (rc) {
+        ekf_sharded_destroy(h);
+        return rc;
+    }
+    *out = h;
+    return 0;
+}
+
+int ekf_sharded_predict(ekf_sharded* h, double dtheta, double dx) {
+    if (!h) return fail(-1, "null handle");
+    Dev g(h->device);
+    for (auto& s : h->sh) {
+        k_sh_motion<<<1, 32, 0, h->stream>>>(s.state, s.rank == 0 ? s.sig : nullptr, h->ld, dtheta, dx, s.motion);
+        h->launches++;
+        int lr_begin = 0;
+        if (s.rank == 0) {
+            k_sh_predict_rows12<<<(h->N - 3 + 255) / 256, 256, 0, h->stream>>>(s.sig, h->ld, h->N, s.motion);
+            h->launches++;
+            lr_begin = 3;
+        }
+        if (s.rows > lr_begin) {
+            k_sh_predict_cols<<<(s.rows - lr_begin + 255) / 256, 256, 0, h->stream>>>(s.sig, h->ld, lr_begin, s.rows, s.motion);
+            h->launches++;
+        }
+    }
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int ekf_sharded_measurement(ekf_sharded* h, const double* xy, const uint8_t* visible) {
+    if (!h || !xy || !visible) return fail(-1, "null argument");
+    Dev g(h->device);
+    const int n = h->n;
+    if (!h->init_flag_host) {
+        CU(cudaStreamSynchronize(h->stream));
+        memcpy(h->h_stage, xy, sizeof(double) * 2 * n);
+        for (auto& s : h->sh) {
+            CU(cudaMemcpyAsync(s.xy, h->h_stage, sizeof(double) * 2 * n, cudaMemcpyHostToDevice, h->stream));
+            k_large_init_landmarks<<<(n + 255) / 256, 256, 0, h->stream>>>(s.state, s.xy, n, s.init_flag);
+            h->launches++;
+        }
+        CU(cudaGetLastError());
+        CU(cudaStreamSynchronize(h->stream));
+        h->init_flag_host = 1;
+    }
+    for (auto& s : h->sh) CU(cudaMemcpyAsync(s.pose0, s.state, 3 * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    for (int i = 0; i < n; ++i) {
+        if (!visible[i]) continue;
+        int rc = correct(h, false, true, i, xy[2 * i], xy[2 * i + 1]);
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+int ekf_sharded_data_association(ekf_sharded* h, const double* xy, int m, uint8_t* known, int32_t* assoc_out,
+                                 double* dmin_out, double* second_out, uint8_t* created_out) {
+    if (!h || !known || m < 0 || (m > 0 && !xy)) return fail(-1, "invalid argument");
+    if (m == 0) return 0;
+    Dev g(h->device);
+    const int n = h->n;
+    int rc = ensure_m(h, m);
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(h->stream));
+    int known_count = 0;
+    while (known_count < n && known[known_count]) ++known_count;
+    double* st_xy = reinterpret_cast<double*>(h->h_stage);
+    memcpy(st_xy, xy, sizeof(double) * 2 * m);
+    int* st_kc = reinterpret_cast<int*>(h->h_stage + sizeof(double) * 2 * m);
+    *st_kc = known_count;
+    for (auto& s : h->sh) {
+        CU(cudaMemcpyAsync(s.meas, st_xy, sizeof(double) * 2 * m, cudaMemcpyHostToDevice, h->stream));
+        CU(cudaMemcpyAsync(s.known_count, st_kc, sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    }
+    for (int j = 0; j < m; ++j) {
+        rc = exchange_robot_rows(h);
+        if (rc) return rc;
+        for (auto& s : h->sh) {
+            k_sh_assoc_local<<<s.assoc_blocks, 256, 0, h->stream>>>(s.robot, s.sig, h->ld, s.r0, s.L0, s.L1, s.state, s.meas, j,
+                                                                     s.known_count, s.blk, s.done, s.part);
+            h->launches++;
+        }
+        CU(cudaGetLastError());
+        rc = exchange_partials(h);
+        if (rc) return rc;
+        for (auto& s : h->sh) {
+            k_sh_decide<<<1, 32, 0, h->stream>>>(s.parts, h->world, s.state, n, s.meas, j, s.known_count, s.cmd, s.d_assoc,
+                                                 s.d_dmin, s.d_second, s.d_created);
+            h->launches++;
+        }
+        CU(cudaGetLastError());
+        rc = correct(h, true, false, 0, 0.0, 0.0);
+        if (rc) return rc;
+    }
+    Shard& s0 = h->sh[0];  // every replica holds the same decisions
+    unsigned char* o = h->h_stage + sizeof(double) * 2 * m + 64;
+    int32_t* o_assoc = reinterpret_cast<int32_t*>(o);
+    double* o_dmin = reinterpret_cast<double*>(o + (((size_t)m * 4 + 15) & ~(size_t)15));
+    double* o_second = o_dmin + m;
+    uint8_t* o_created = reinterpret_cast<uint8_t*>(o_second + m);
+    int* o_kc = reinterpret_cast<int*>(o_created + ((m + 15) & ~15));
+    CU(cudaMemcpyAsync(o_assoc, s0.d_assoc, sizeof(int32_t) * m, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaMemcpyAsync(o_dmin, s0.d_dmin, sizeof(double) * m, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaMemcpyAsync(o_second, s0.d_second, sizeof(double) * m, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaMemcpyAsync(o_created, s0.d_created, m, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaMemcpyAsync(o_kc, s0.known_count, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    if (assoc_out) memcpy(assoc_out, o_assoc, sizeof(int32_t) * m);
+    if (dmin_out) memcpy(dmin_out, o_dmin, sizeof(double) * m);
+    if (second_out) memcpy(second_out, o_second, sizeof(double) * m);
+    if (created_out) memcpy(created_out, o_created, m);
+    for (int i = known_count; i < *o_kc && i < n; ++i) known[i] = 1;
+    return 0;
+}
+
+int ekf_sharded_get_state(ekf_sharded* h, double* out) {
+    if (!h || !out) return fail(-1, "null argument");
+    Dev g(h->device);
+    CU(cudaMemcpyAsync(out, h->sh[0].state, sizeof(double) * h->N, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+int ekf_sharded_rows(ekf_sharded* h, int shard, int64_t* row_begin, int64_t* row_end) {
+    if (!h || shard < 0 || shard >= (int)h->sh.size()) return fail(-1, "invalid shard");
+    if (row_begin) *row_begin = h->sh[shard].r0;
+    if (row_end) *row_end = h->sh[shard].r1;
+    return 0;
+}
+int ekf_sharded_get_sigma_rows(ekf_sharded* h, int shard, double* out, int64_t ld) {
+    if (!h || !out || shard < 0 || shard >= (int)h->sh.size() || ld < h->N) return fail(-1, "invalid argument");
+    Dev g(h->device);
+    Shard& s = h->sh[shard];
+    if (s.rows > 0)
+        CU(cudaMemcpy2DAsync(out, sizeof(double) * ld, s.sig, sizeof(double) * h->ld, sizeof(double) * h->N, s.rows,
+                             cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+int ekf_sharded_update_count(ekf_sharded* h, uint64_t* out) {
+    if (!h || !out) return fail(-1, "null argument");
+    Dev g(h->device);
+    unsigned long long v = 0;
+    CU(cudaMemcpyAsync(&v, h->sh[0].nupd, sizeof(v), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    *out = v;
+    return 0;
+}
+int ekf_sharded_launch_count(ekf_sharded* h, uint64_t* out) {
+    if (!h || !out) return fail(-1, "null argument");
+    *out = h->launches;
+    return 0;
+}
+int ekf_sharded_sync(ekf_sharded* h) {
+    if (!h) return fail(-1, "null handle");
+    Dev g(h->device);
+    CU(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+int ekf_sharded_timer_start(ekf_sharded* h) {
+    if (!h) return fail(-1, "null handle");
+    Dev g(h->device);
+    if (!h->t0) {
+        CU(cudaEventCreate(&h->t0));
+        CU(cudaEventCreate(&h->t1));
+    }
+    CU(cudaEventRecord(h->t0, h->stream));
+    return 0;
+}
+int ekf_sharded_timer_stop(ekf_sharded* h, float* ms_out) {
+    if (!h || !ms_out || !h->t0) return fail(-1, "timer not started");
+    Dev g(h->device);
+    CU(cudaEventRecord(h->t1, h->stream));
+    CU(cudaEventSynchronize(h->t1));
+    CU(cudaEventElapsedTime(ms_out, h->t0, h->t1));
+    return 0;
+}
+
+}  // extern "C"

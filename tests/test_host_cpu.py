@@ -24,12 +24,14 @@ def declared_symbols():
 
 def test_library_exports_every_declared_symbol(pkg):
     lib = pkg._lib.load()
+    lib_sh = pkg._lib.load_sharded()
     decl = declared_symbols()
-    assert len(decl) > 60
-    missing = [n for n in sorted(decl) if not hasattr(lib, n)]
+    assert len(decl) > 80
+    missing = [n for n in sorted(decl) if not hasattr(lib_sh if n.startswith("ekf_sharded_") else lib, n)]
     assert not missing, missing
-    # and the Python binding table covers the same set (header, library and binding in step)
-    assert set(pkg._lib.SIGNATURES) == decl, set(pkg._lib.SIGNATURES) ^ decl
+    # and the Python binding tables cover the same set (headers, libraries and bindings in step)
+    bound = set(pkg._lib.SIGNATURES) | set(pkg._lib.SIGNATURES_SHARDED)
+    assert bound == decl, bound ^ decl
 
 
 def test_no_gpu_means_loud_failure_not_fallback(pkg):
