@@ -317,11 +317,12 @@ def simulate_unknown(world: World, B: int, steps: int, seed: int = 0, first_filt
         if not shuffle:
             key = np.broadcast_to(np.arange(nt, dtype=np.float64)[None, :] / nt, key.shape)
         key = np.where(v, key, 2.0)  # invisible last
-        order = np.argsort(key, axis=1, kind="stable")[:, :m_max]
-        c = np.minimum(v.sum(axis=1), m_max)
-        sel = np.arange(m_max)[None, :] < c[:, None]
-        meas[t, :, :, 0] = np.where(sel, np.take_along_axis(rx, order, axis=1), 0.0)
-        meas[t, :, :, 1] = np.where(sel, np.take_along_axis(ry, order, axis=1), 0.0)
+        me = min(m_max, nt)
+        order = np.argsort(key, axis=1, kind="stable")[:, :me]
+        c = np.minimum(v.sum(axis=1), me)
+        sel = np.arange(me)[None, :] < c[:, None]
+        meas[t, :, :me, 0] = np.where(sel, np.take_along_axis(rx, order, axis=1), 0.0)
+        meas[t, :, :me, 1] = np.where(sel, np.take_along_axis(ry, order, axis=1), 0.0)
         cnt[t] = c
         truth[t, :, 0], truth[t, :, 1], truth[t, :, 2] = sim.x, sim.y, sim.th
     return {"twists": tw, "meas": meas, "count": cnt, "truth": truth}
