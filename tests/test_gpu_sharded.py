@@ -105,7 +105,7 @@ err_s = sigma_err_rows = float(np.max(np.abs(f.sigma_rows(0) - o.sigma[a:b]) / n
 err_x = state_err(f.state, o.state)
 assert err_x < 1e-9 and err_s < 1e-9, (rank, err_x, err_s)
 dist.barrier()
-print("rank", rank, "rows", (a, b), "ok", err_x, err_s, flush=True)
+sys.stdout.write("RANK%dOK rows=(%d,%d) err_state=%.2e err_sigma=%.2e\n" % (rank, a, b, err_x, err_s)); sys.stdout.flush()
 f.close()
 dist.destroy_process_group()
 '''
@@ -121,4 +121,4 @@ def test_nccl_two_ranks(gpu_pkg, tmp_path):
                         "--master-addr", "127.0.0.1", "--master-port", "29688", str(script), ROOT],
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
-    assert "rank 0" in r.stdout and "rank 1" in r.stdout
+    assert "RANK0OK" in r.stdout and "RANK1OK" in r.stdout, r.stdout[-2000:]
