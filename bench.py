@@ -228,6 +228,52 @@ def large_map_leg(pkg, device, n_lm, timed_updates, peak_gbs, want_cpu):
     return out
 
 
+def sharded_map_leg(pkg, dist, local, n_lm, timed_updates, peak_gbs):
+    """cfg5: one filter, n_lm landmarks, Sigma row-block-sharded over all ranks (NCCL all-reduce of W and all-gather
+    of K per correction).  Timed on the device, max over ranks."""
+    from ekf_slam_ml_b200.sharded import ShardedEKF
+    tg = pkg.tracegen
+    world = dist.get_world_size()
+    nx = int(round(np.sqrt(n_lm)))
+    assert nx * nx == n_lm, "sharded map expects a square grid"
+    w = tg.grid_world(nx, nx, pitch=0.5, n_slots=n_lm, max_visible=0.7)
+    steps = 40
+    tr = tg.simulate_known(w, 1, steps, seed=77)
+    f = ShardedEKF.from_process_group(n_lm, dist, local)
+    N = 3 + 2 * n_lm
+    done, t, total_ms = 0, 0, 0.0
+    l0 = None
+    while t < steps and done < timed_updates:
+        nvis = int(tr["vis"][t, 0].sum())
+        timed = t >= 2
+        if timed and l0 is None:
+            l0 = f.launch_count
+        if timed and nvis:
+            f.sync()
+            dist.barrier()
+            f.timer_start()
+        f.prediction(tuple(tr["twists"][t, 0]))
+        f.measurement(tr["xy"][t, 0], tr["vis"][t, 0])
+        if timed and nvis:
+            total_ms += pkg.sharding.allreduce_max(f.timer_stop(), dist, "cuda")
+            done += nvis
+        t += 1
+    ms_upd = total_ms / max(done, 1)
+    rows = f.rows(0)
+    per_gpu_bytes = 16.0 * N * N / world
+    out = {
+        "workload": f"cfg5: single map, n={n_lm} landmarks (N={N}, Sigma {8.0 * N * N / 1e9:.1f} GB) row-block-sharded over "
+                    f"{world} GPUs; per correction: NCCL all-reduce of W (2N fp64) + all-gather of K (2N fp64), sweep of own rows",
+        "value": 1e3 / ms_upd, "unit": UNIT, "updates_timed": done, "ms_per_update": ms_upd,
+        "gpu_launches_rank0": int(f.launch_count - (l0 or 0)), "rows_rank0": list(rows),
+        "roofline": {"bound": "hbm", "achieved": per_gpu_bytes / (ms_upd * 1e-3) / 1e9, "peak": peak_gbs, "unit": "GB/s per GPU",
+                     "frac": per_gpu_bytes / (ms_upd * 1e-3) / 1e9 / peak_gbs, "traffic": None,
+                     "algorithmic_bytes_per_update_per_gpu": per_gpu_bytes},
+    }
+    f.close()
+    return out
+
+
 def run_ours(args):
     import ekf_slam_ml_b200 as pkg
     rank = int(os.environ.get("RANK", "0"))
@@ -383,6 +429,13 @@ def run_ours(args):
             del d_tw, d_xy, d_vis
             torch.cuda.empty_cache()
             line["large_map"] = large_map_leg(pkg, local, args.large_n, args.large_updates, peak_gbs, want_cpu=True)
+    if world > 1 and not args.skip_large:
+        # cfg5 needs every rank: free the batch first (Sigma shard = 51.2 GB / world per GPU)
+        bt.close()
+        del d_tw, d_xy, d_vis
+        torch.cuda.empty_cache()
+        sm = sharded_map_leg(pkg, dist, local, args.sharded_n, args.sharded_updates, peak_gbs)
+        line["sharded_map"] = sm
     if rank == 0:
         print(json.dumps(line), flush=True)
     if dist:
@@ -400,6 +453,8 @@ def main():
     ap.add_argument("--large-n", type=int, default=8192)
     ap.add_argument("--large-updates", type=int, default=200)
     ap.add_argument("--skip-large", action="store_true")
+    ap.add_argument("--sharded-n", type=int, default=40000, help="cfg5 landmarks (square number), N>1 only")
+    ap.add_argument("--sharded-updates", type=int, default=50)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)
