@@ -54,6 +54,9 @@ class ClockSampler:
             self.nv = pynvml
             self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
             self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            pynvml.nvmlDeviceGetClockInfo(self.h, pynvml.NVML_CLOCK_SM)  # first query is slow: take it now
+            if hasattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons"):
+                pynvml.nvmlDeviceGetCurrentClocksEventReasons(self.h)
         except Exception as e:  # NVML missing: report that, do not invent numbers
             self.nv = None
             self.err = repr(e)
@@ -72,7 +75,7 @@ class ClockSampler:
                         self.reasons.add(k)
             except Exception:
                 pass
-            time.sleep(0.001)
+            time.sleep(0.0002)
 
     def start(self):
         if self.nv:
