@@ -13,6 +13,7 @@
 #include "../../include/ekf_slam_b200.h"
 #include "ekf_fused.cuh"
 #include "ekf_large.cuh"
+#include "ekf_large_delayed.cuh"
 
 using namespace ekf;
 
@@ -172,8 +173,10 @@ struct ekf_filter {
     unsigned char* h_out = nullptr;  // pinned output staging
     size_t h_out_bytes = 0;
     // stream engine scratch
-    double2* d_K2 = nullptr;
-    double2* d_W2 = nullptr;
+    double2* d_K2 = nullptr;  // [kMaxPending][ld] pending gain factors
+    double2* d_W2 = nullptr;  // [kMaxPending][ld] pending H*Sigma factors
+    double* d_state_alt = nullptr;  // ping-pong partner of d_state (the gain kernel never writes what it reads)
+    int pending = 0;                // corrections computed but not yet applied to Sigma
     double* d_motion = nullptr;
     double* d_pose0 = nullptr;
     UpdateCmd* d_cmd = nullptr;
@@ -207,6 +210,7 @@ int free_filter(ekf_filter* h) {
     cudaFree(h->d_scalar);
     cudaFree(h->d_K2);
     cudaFree(h->d_W2);
+    cudaFree(h->d_state_alt);
     cudaFree(h->d_motion);
     cudaFree(h->d_pose0);
     cudaFree(h->d_cmd);
@@ -310,15 +314,27 @@ int sweep_grid(const ekf_filter* h) {
     return (int)std::max(1LL, std::min(tiles, cap));
 }
 
-// one landmark correction on the stream engine: gain then sweep
+// Apply the pending factors to Sigma in one sweep (ekf_large_delayed.cuh).
+int stream_flush(ekf_filter* h, int n_counted, const UpdateCmd* cmd) {
+    if (h->pending == 0) return EKF_OK;
+    CU(launch_sweep_p(h->pending, h->d_sigma, h->ld, h->N, h->d_K2, h->d_W2, 0, h->d_nupd, n_counted, cmd, h->sm_count,
+                      h->stream));
+    h->launches += 1;
+    h->pending = 0;
+    return EKF_OK;
+}
+
+// One landmark correction on the stream engine: the gain kernel appends a factor pair; Sigma itself is only
+// touched when kMaxPending factors have piled up or the verb ends.
 int stream_correct(ekf_filter* h, const double* pose_src, const UpdateCmd* cmd, int lm, double sx, double sy) {
     const int gb = (int)((h->ld + 255) / 256);
-    k_large_gain<<<gb, 256, 0, h->stream>>>(h->d_sigma, h->ld, h->N, h->d_state, pose_src, cmd, lm, sx, sy, h->d_K2,
-                                            h->d_W2, h->d_sp);
-    k_large_sweep<<<sweep_grid(h), kSweepThreads, 0, h->stream>>>(h->d_sigma, h->ld, h->N, h->d_K2, h->d_W2, cmd,
-                                                                  h->d_sp, h->d_state, h->d_nupd);
-    h->launches += 2;
+    k_large_gain_p<<<gb, 256, 0, h->stream>>>(h->d_sigma, h->ld, h->N, h->d_state, h->d_state_alt, pose_src, cmd, lm, sx, sy,
+                                              h->d_K2, h->d_W2, h->pending);
+    h->launches += 1;
     CU(cudaGetLastError());
+    std::swap(h->d_state, h->d_state_alt);
+    h->pending += 1;
+    if (h->pending == kMaxPending) return stream_flush(h, cmd ? 0 : kMaxPending, nullptr);
     return EKF_OK;
 }
 
@@ -409,8 +425,10 @@ int ekf_create_ex(int n, int device, int engine, ekf_filter** out) {
         CUH(cudaMemsetAsync(h->d_state, 0, sizeof(double) * h->st_stride, h->stream));
         CUH(cudaMemsetAsync(h->d_init_flag, 0, sizeof(int32_t), h->stream));
         k_large_init_sigma<<<(h->N + 255) / 256, 256, 0, h->stream>>>(h->d_sigma, h->ld, h->N);
-        CUH(cudaMalloc(&h->d_K2, sizeof(double2) * (size_t)h->ld));
-        CUH(cudaMalloc(&h->d_W2, sizeof(double2) * (size_t)h->ld));
+        CUH(cudaMalloc(&h->d_K2, sizeof(double2) * (size_t)h->ld * kMaxPending));
+        CUH(cudaMalloc(&h->d_W2, sizeof(double2) * (size_t)h->ld * kMaxPending));
+        CUH(cudaMalloc(&h->d_state_alt, sizeof(double) * h->st_stride));
+        CUH(cudaMemsetAsync(h->d_state_alt, 0, sizeof(double) * h->st_stride, h->stream));
         CUH(cudaMalloc(&h->d_motion, 2 * sizeof(double)));
         CUH(cudaMalloc(&h->d_pose0, 3 * sizeof(double)));
         CUH(cudaMalloc(&h->d_cmd, sizeof(UpdateCmd)));
@@ -422,8 +440,8 @@ int ekf_create_ex(int n, int device, int engine, ekf_filter** out) {
         CUH(cudaMemsetAsync(h->d_done, 0, sizeof(unsigned int), h->stream));
         CUH(cudaMemsetAsync(h->d_sp, 0, sizeof(Special5), h->stream));
         CUH(cudaMemsetAsync(h->d_cmd, 0, sizeof(UpdateCmd), h->stream));
-        CUH(cudaMemsetAsync(h->d_K2, 0, sizeof(double2) * (size_t)h->ld, h->stream));
-        CUH(cudaMemsetAsync(h->d_W2, 0, sizeof(double2) * (size_t)h->ld, h->stream));
+        CUH(cudaMemsetAsync(h->d_K2, 0, sizeof(double2) * (size_t)h->ld * kMaxPending, h->stream));
+        CUH(cudaMemsetAsync(h->d_W2, 0, sizeof(double2) * (size_t)h->ld * kMaxPending, h->stream));
     }
     h->launches += 1;
     CUH(cudaGetLastError());
@@ -524,7 +542,7 @@ int ekf_measurement(ekf_filter* h, const double* xy, const uint8_t* visible) {
         int rc = stream_correct(h, h->d_pose0, nullptr, i, xy[2 * i], xy[2 * i + 1]);
         if (rc) return rc;
     }
-    return EKF_OK;
+    return stream_flush(h, h->pending, nullptr);
 }
 
 int ekf_data_association(ekf_filter* h, const double* xy, int m, uint8_t* known, int32_t* assoc_out,
@@ -563,7 +581,10 @@ int ekf_data_association(ekf_filter* h, const double* xy, int m, uint8_t* known,
                                                                    h->d_known_count, h->d_partials, h->d_done, h->d_cmd,
                                                                    h->d_assoc, h->d_dmin, h->d_second, h->d_created);
             h->launches += 1;
+            // the next measurement's distances need the corrected Sigma: one factor, applied at once
             rc = stream_correct(h, h->d_state, h->d_cmd, 0, 0.0, 0.0);
+            if (rc) return rc;
+            rc = stream_flush(h, 1, h->d_cmd);
             if (rc) return rc;
         }
     }

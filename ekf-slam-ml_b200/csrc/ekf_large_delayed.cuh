@@ -1,0 +1,239 @@
+// Delayed application of the rank-2 covariance updates of the streamed engine.
+//
+// The reference applies Sigma <- Sigma - K W after every landmark correction (ekf_slam.cpp:191-192); for a large
+// map that is one full HBM read + write of Sigma per correction.  Here up to kMaxPending corrections are kept as
+// factor pairs (K_j, W_j) and applied in ONE sweep:  Sigma <- Sigma - sum_j K_j W_j.  The next correction only needs
+// five rows and five columns of the CURRENT covariance; they are rebuilt on the fly from Sigma_0 and the pending
+// factors.  Every element goes through exactly the same sequence of FMAs as with sequential sweeps
+// (v = fma(-k.y, w.y, fma(-k.x, w.x, v)) for j = 0, 1, ...), so the result is bit-identical — only the HBM traffic
+// changes: 16 N^2 bytes per SWEEP instead of per correction.
+#pragma once
+#include "ekf_large.cuh"
+
+namespace ekf {
+
+constexpr int kMaxPending = 8;
+
+struct GainSharedP {
+    Hj h;
+    Sym2 si;
+    double nu0, nu1;
+    int i3;
+    int active;
+    double2 Kidx[kMaxPending][5];  // K_j[idx_l]
+    double2 Widx[kMaxPending][5];  // W_j[idx_l]
+};
+
+__device__ __forceinline__ double apply_factor(double v, double2 k, double2 w) {
+    return fma(-k.y, w.y, fma(-k.x, w.x, v));
+}
+
+// Correction number `p` of the current group: writes (K_p, W_p), reads Sigma_0 and the factors j < p.
+// state_in is never written (the new state goes to state_out), so no CTA can observe a half-updated state.
+__global__ void __launch_bounds__(256)
+    k_large_gain_p(const double* __restrict__ sig, long long ld, int N, const double* __restrict__ state_in,
+                   double* __restrict__ state_out, const double* __restrict__ pose_src, const UpdateCmd* __restrict__ cmd,
+                   int lm_arg, double sx_arg, double sy_arg, double2* __restrict__ Kp, double2* __restrict__ Wp, int p) {
+    __shared__ GainSharedP g;
+    if (threadIdx.x == 0) {
+        int lm = lm_arg;
+        double sx = sx_arg, sy = sy_arg;
+        int active = 1;
+        if (cmd) {
+            active = cmd->do_update;
+            lm = cmd->lm;
+            sx = cmd->sx;
+            sy = cmd->sy;
+        }
+        g.active = active;
+        if (active) {
+            const int i3 = 3 + 2 * lm;
+            const double theta = pose_src[0], x = pose_src[1], y = pose_src[2];
+            const Hj h = make_hj(state_in[i3], state_in[i3 + 1], theta, x, y);
+            const long long id[5] = {0, 1, 2, i3, i3 + 1};
+            for (int j = 0; j < p; ++j)
+                for (int l = 0; l < 5; ++l) {
+                    g.Kidx[j][l] = Kp[(long long)j * ld + id[l]];
+                    g.Widx[j][l] = Wp[(long long)j * ld + id[l]];
+                }
+            double w0[5], w1[5];
+            for (int l = 0; l < 5; ++l) {
+                double s[5];
+                for (int a = 0; a < 5; ++a) {
+                    double v = sig[id[a] * ld + id[l]];
+                    for (int j = 0; j < p; ++j) v = apply_factor(v, g.Kidx[j][a], g.Widx[j][l]);
+                    s[a] = v;
+                }
+                w0[l] = h_row0(h, s[1], s[2], s[3], s[4]);
+                w1[l] = h_row1(h, s[0], s[1], s[2], s[3], s[4]);
+            }
+            const double s00 = h_row0(h, w0[1], w0[2], w0[3], w0[4]) + kR;
+            const double s01 = h_row1(h, w0[0], w0[1], w0[2], w0[3], w0[4]);
+            const double s10 = h_row0(h, w1[1], w1[2], w1[3], w1[4]);
+            const double s11 = h_row1(h, w1[0], w1[1], w1[2], w1[3], w1[4]) + kR;
+            g.h = h;
+            g.si = inv2x2(s00, s01, s10, s11);
+            double zr, zphi;
+            range_bearing(sx, sy, zr, zphi);
+            g.nu0 = __dsub_rn(zr, h.zr);
+            g.nu1 = normalize_angle(__dsub_rn(zphi, h.zphi));
+            g.i3 = i3;
+        }
+    }
+    __syncthreads();
+    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= ld) return;
+    double2* Kout = Kp + (long long)p * ld;
+    double2* Wout = Wp + (long long)p * ld;
+    if (k >= N || !g.active) {  // padding entries and dropped measurements contribute a zero factor
+        Kout[k] = make_double2(0.0, 0.0);
+        Wout[k] = make_double2(0.0, 0.0);
+        if (k < N) state_out[k] = state_in[k];
+        return;
+    }
+    const Hj h = g.h;
+    const int i3 = g.i3, i4 = i3 + 1;
+    double s0 = sig[k], s1 = sig[ld + k], s2 = sig[2 * ld + k], s3 = sig[i3 * ld + k], s4 = sig[i4 * ld + k];
+    const double* row = sig + k * ld;
+    double r0 = row[0], r1 = row[1], r2 = row[2], r3 = row[i3], r4 = row[i4];
+    for (int j = 0; j < p; ++j) {
+        const double2 wj = Wp[(long long)j * ld + k];  // W_j[:, k]
+        const double2 kj = Kp[(long long)j * ld + k];  // K_j[k, :]
+        s0 = apply_factor(s0, g.Kidx[j][0], wj);
+        s1 = apply_factor(s1, g.Kidx[j][1], wj);
+        s2 = apply_factor(s2, g.Kidx[j][2], wj);
+        s3 = apply_factor(s3, g.Kidx[j][3], wj);
+        s4 = apply_factor(s4, g.Kidx[j][4], wj);
+        r0 = apply_factor(r0, kj, g.Widx[j][0]);
+        r1 = apply_factor(r1, kj, g.Widx[j][1]);
+        r2 = apply_factor(r2, kj, g.Widx[j][2]);
+        r3 = apply_factor(r3, kj, g.Widx[j][3]);
+        r4 = apply_factor(r4, kj, g.Widx[j][4]);
+    }
+    Wout[k] = make_double2(h_row0(h, s1, s2, s3, s4), h_row1(h, s0, s1, s2, s3, s4));
+    const double p0 = h_row0(h, r1, r2, r3, r4), p1 = h_row1(h, r0, r1, r2, r3, r4);
+    const double k0 = fma(p1, g.si.i10, p0 * g.si.i00);
+    const double k1 = fma(p1, g.si.i11, p0 * g.si.i01);
+    Kout[k] = make_double2(k0, k1);
+    double ns = state_in[k] + fma(k1, g.nu1, k0 * g.nu0);
+    if (k == 0) ns = normalize_angle(ns);  // ekf_slam.cpp:187
+    state_out[k] = ns;
+}
+
+// Sigma[r][c] <- Sigma[r][c] - sum_{j<P} K_j[r] W_j[c], one pass over Sigma.  COLS columns per thread (4 -> 256-bit
+// accesses, 2 -> 128-bit) so that the P x COLS W-pairs stay in registers for the whole tile.
+template <int P, int COLS>
+__global__ void __launch_bounds__(kSweepThreads)
+    k_large_sweep_p(double* __restrict__ sig, long long ld, int n_rows, const double2* __restrict__ Kp,
+                    const double2* __restrict__ Wp, long long row0, unsigned long long* __restrict__ n_updates,
+                    int n_counted, const UpdateCmd* __restrict__ cmd) {
+    if (cmd && !cmd->do_update) return;  // association dropped the measurement: nothing to apply (P == 1 there)
+    if (blockIdx.x == 0 && threadIdx.x == 0 && n_updates) *n_updates += (unsigned long long)n_counted;
+    constexpr int CHUNK = kSweepThreads * COLS;
+    const int chunks = (int)((ld + CHUNK - 1) / CHUNK);
+    const int row_blocks = (n_rows + kSweepRows - 1) / kSweepRows;
+    const long long tiles = (long long)chunks * row_blocks;
+    for (long long t = blockIdx.x; t < tiles; t += gridDim.x) {
+        const int rb = (int)(t / chunks), cc = (int)(t - (long long)rb * chunks);
+        const long long c = (long long)cc * CHUNK + threadIdx.x * COLS;
+        if (c >= ld) continue;
+        double2 w[P][COLS];
+#pragma unroll
+        for (int j = 0; j < P; ++j)
+#pragma unroll
+            for (int q = 0; q < COLS; ++q) w[j][q] = Wp[(long long)j * ld + c + q];
+        const int r_begin = rb * kSweepRows;
+        const int r_end = min(n_rows, r_begin + kSweepRows);
+        double* ptr = sig + (long long)r_begin * ld + c;
+        constexpr int U = (P * COLS <= 8) ? 4 : 2;  // rows in flight per thread
+        int r = r_begin;
+        for (; r + U <= r_end; r += U) {
+            double v[U][COLS];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (COLS == 4) {
+                    ld256(ptr + u * ld, v[u][0], v[u][1], v[u][2], v[u][3]);
+                } else {
+                    const double2 t2 = *reinterpret_cast<const double2*>(ptr + u * ld);
+                    v[u][0] = t2.x;
+                    v[u][1] = t2.y;
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+#pragma unroll
+                for (int j = 0; j < P; ++j) {
+                    const double2 k = Kp[(long long)j * ld + row0 + r + u];
+#pragma unroll
+                    for (int q = 0; q < COLS; ++q) v[u][q] = apply_factor(v[u][q], k, w[j][q]);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (COLS == 4) {
+                    st256(ptr + u * ld, v[u][0], v[u][1], v[u][2], v[u][3]);
+                } else {
+                    *reinterpret_cast<double2*>(ptr + u * ld) = make_double2(v[u][0], v[u][1]);
+                }
+            }
+            ptr += (long long)U * ld;
+        }
+        for (; r < r_end; ++r) {
+            double v[COLS];
+            if (COLS == 4) {
+                ld256(ptr, v[0], v[1], v[2], v[3]);
+            } else {
+                const double2 t2 = *reinterpret_cast<const double2*>(ptr);
+                v[0] = t2.x;
+                v[1] = t2.y;
+            }
+#pragma unroll
+            for (int j = 0; j < P; ++j) {
+                const double2 k = Kp[(long long)j * ld + row0 + r];
+#pragma unroll
+                for (int q = 0; q < COLS; ++q) v[q] = apply_factor(v[q], k, w[j][q]);
+            }
+            if (COLS == 4) {
+                st256(ptr, v[0], v[1], v[2], v[3]);
+            } else {
+                *reinterpret_cast<double2*>(ptr) = make_double2(v[0], v[1]);
+            }
+            ptr += ld;
+        }
+    }
+}
+
+// Launch the sweep instantiation for `pending` factors.  grid_cap = SM count x resident CTAs.
+inline cudaError_t launch_sweep_p(int pending, double* sig, long long ld, int n_rows, const double2* Kp, const double2* Wp,
+                                  long long row0, unsigned long long* n_updates, int n_counted, const UpdateCmd* cmd,
+                                  int sm_count, cudaStream_t stream) {
+    auto grid_for = [&](int cols) {
+        const long long chunk = (long long)kSweepThreads * cols;
+        const long long chunks = (ld + chunk - 1) / chunk;
+        const long long row_blocks = (n_rows + kSweepRows - 1) / kSweepRows;
+        const long long tiles = chunks * row_blocks;
+        long long g = tiles < (long long)sm_count * 8 ? tiles : (long long)sm_count * 8;
+        return (unsigned)(g < 1 ? 1 : g);
+    };
+#define EKF_SWEEP_CASE(PP, CC)                                                                                       \
+    case PP:                                                                                                         \
+        k_large_sweep_p<PP, CC><<<grid_for(CC), kSweepThreads, 0, stream>>>(sig, ld, n_rows, Kp, Wp, row0, n_updates, \
+                                                                             n_counted, cmd);                        \
+        break;
+    switch (pending) {
+        EKF_SWEEP_CASE(1, 4)
+        EKF_SWEEP_CASE(2, 4)
+        EKF_SWEEP_CASE(3, 4)
+        EKF_SWEEP_CASE(4, 4)
+        EKF_SWEEP_CASE(5, 2)
+        EKF_SWEEP_CASE(6, 2)
+        EKF_SWEEP_CASE(7, 2)
+        EKF_SWEEP_CASE(8, 2)
+        default:
+            return cudaErrorInvalidValue;
+    }
+#undef EKF_SWEEP_CASE
+    return cudaGetLastError();
+}
+
+}  // namespace ekf
