@@ -129,9 +129,9 @@ __global__ void __launch_bounds__(kSweepThreads)
                     int n_counted, const UpdateCmd* __restrict__ cmd) {
     if (cmd && !cmd->do_update) return;  // association dropped the measurement: nothing to apply (P == 1 there)
     if (blockIdx.x == 0 && threadIdx.x == 0 && n_updates) *n_updates += (unsigned long long)n_counted;
-    constexpr int CHUNK = kSweepThreads * COLS;
+    constexpr int CHUNK = THREADS * COLS;
     const int chunks = (int)((ld + CHUNK - 1) / CHUNK);
-    const int row_blocks = (n_rows + kSweepRows - 1) / kSweepRows;
+    const int row_blocks = (n_rows + ROWS - 1) / ROWS;
     const long long tiles = (long long)chunks * row_blocks;
     for (long long t = blockIdx.x; t < tiles; t += gridDim.x) {
         const int rb = (int)(t / chunks), cc = (int)(t - (long long)rb * chunks);
@@ -203,36 +203,32 @@ __global__ void __launch_bounds__(kSweepThreads)
     }
 }
 
-// Launch the sweep instantiation for `pending` factors.  grid_cap = SM count x resident CTAs.
+// Launch the sweep instantiation for `pending` factors.  One CTA per tile (ROWS x THREADS*4 columns): on B200 the
+// plain full grid beats a persistent grid-stride launch here (scripts/sweep_tune.cu: P=1 0.65 ms = 6.6 TB/s at
+// N = 16,387; P=4..6 0.79-0.82 ms; P=8 0.98 ms — the FMAs of a tile do not overlap its own loads).
+template <int P, int U, int ROWS, int THREADS>
+inline void launch_sweep_cfg(double* sig, long long ld, int n_rows, const double2* Kp, const double2* Wp, long long row0,
+                             unsigned long long* n_updates, int n_counted, const UpdateCmd* cmd, cudaStream_t stream) {
+    const long long chunk = (long long)THREADS * 4;
+    const long long tiles = ((ld + chunk - 1) / chunk) * ((n_rows + ROWS - 1) / ROWS);
+    k_large_sweep_p<P, 4, U, ROWS, THREADS><<<(unsigned)(tiles < 1 ? 1 : tiles), THREADS, 0, stream>>>(
+        sig, ld, n_rows, Kp, Wp, row0, n_updates, n_counted, cmd);
+}
+
 inline cudaError_t launch_sweep_p(int pending, double* sig, long long ld, int n_rows, const double2* Kp, const double2* Wp,
                                   long long row0, unsigned long long* n_updates, int n_counted, const UpdateCmd* cmd,
-                                  int sm_count, cudaStream_t stream) {
-    auto grid_for = [&](int cols) {
-        const long long chunk = (long long)kSweepThreads * cols;
-        const long long chunks = (ld + chunk - 1) / chunk;
-        const long long row_blocks = (n_rows + kSweepRows - 1) / kSweepRows;
-        const long long tiles = chunks * row_blocks;
-        long long g = tiles < (long long)sm_count * 8 ? tiles : (long long)sm_count * 8;
-        return (unsigned)(g < 1 ? 1 : g);
-    };
-#define EKF_SWEEP_CASE(PP, CC)                                                                                       \
-    case PP:                                                                                                         \
-        k_large_sweep_p<PP, CC><<<grid_for(CC), kSweepThreads, 0, stream>>>(sig, ld, n_rows, Kp, Wp, row0, n_updates, \
-                                                                             n_counted, cmd);                        \
-        break;
+                                  int /*sm_count*/, cudaStream_t stream) {
     switch (pending) {
-        EKF_SWEEP_CASE(1, 4)
-        EKF_SWEEP_CASE(2, 4)
-        EKF_SWEEP_CASE(3, 4)
-        EKF_SWEEP_CASE(4, 4)
-        EKF_SWEEP_CASE(5, 2)
-        EKF_SWEEP_CASE(6, 2)
-        EKF_SWEEP_CASE(7, 2)
-        EKF_SWEEP_CASE(8, 2)
-        default:
-            return cudaErrorInvalidValue;
+        case 1: launch_sweep_cfg<1, 4, 32, 256>(sig, ld, n_rows, Kp, Wp, row0, n_updates, n_counted, cmd, stream); break;
+        case 2: launch_sweep_cfg<2, 4, 32, 256>(sig, ld, n_rows, Kp, Wp, row0, n_updates, n_counted, cmd, stream); break;
+        case 3: launch_sweep_cfg<3, 4, 64, 128>(sig, ld, n_rows, Kp, Wp, row0, n_updates, n_counted, cmd, stream); break;
+        case 4: launch_sweep_cfg<4, 4, 64, 128>(sig, ld, n_rows, Kp, Wp, row0, n_updates, n_counted, cmd, stream); break;
+        case 5: launch_sweep_cfg<5, 4, 64, 128>(sig, ld, n_rows, Kp, Wp, row0, n_updates, n_counted, cmd, stream); break;
+        case 6: launch_sweep_cfg<6, 4, 64, 128>(sig, ld, n_rows, Kp, Wp, row0, n_updates, n_counted, cmd, stream); break;
+        case 7: launch_sweep_cfg<7, 4, 128, 128>(sig, ld, n_rows, Kp, Wp, row0, n_updates, n_counted, cmd, stream); break;
+        case 8: launch_sweep_cfg<8, 4, 64, 128>(sig, ld, n_rows, Kp, Wp, row0, n_updates, n_counted, cmd, stream); break;
+        default: return cudaErrorInvalidValue;
     }
-#undef EKF_SWEEP_CASE
     return cudaGetLastError();
 }
 
