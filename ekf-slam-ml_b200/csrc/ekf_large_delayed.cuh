@@ -122,8 +122,8 @@ __global__ void __launch_bounds__(256)
 
 // Sigma[r][c] <- Sigma[r][c] - sum_{j<P} K_j[r] W_j[c], one pass over Sigma.  COLS columns per thread (4 -> 256-bit
 // accesses, 2 -> 128-bit) so that the P x COLS W-pairs stay in registers for the whole tile.
-template <int P, int COLS>
-__global__ void __launch_bounds__(kSweepThreads)
+template <int P, int COLS, int U, int ROWS, int THREADS>
+__global__ void __launch_bounds__(THREADS, 1)
     k_large_sweep_p(double* __restrict__ sig, long long ld, int n_rows, const double2* __restrict__ Kp,
                     const double2* __restrict__ Wp, long long row0, unsigned long long* __restrict__ n_updates,
                     int n_counted, const UpdateCmd* __restrict__ cmd) {
@@ -142,10 +142,10 @@ __global__ void __launch_bounds__(kSweepThreads)
         for (int j = 0; j < P; ++j)
 #pragma unroll
             for (int q = 0; q < COLS; ++q) w[j][q] = Wp[(long long)j * ld + c + q];
-        const int r_begin = rb * kSweepRows;
-        const int r_end = min(n_rows, r_begin + kSweepRows);
+        const int r_begin = rb * ROWS;
+        const int r_end = min(n_rows, r_begin + ROWS);
         double* ptr = sig + (long long)r_begin * ld + c;
-        constexpr int U = (P * COLS <= 8) ? 4 : 2;  // rows in flight per thread
+        // U rows (U x 32 B of loads) in flight per thread
         int r = r_begin;
         for (; r + U <= r_end; r += U) {
             double v[U][COLS];
