@@ -11,6 +11,10 @@
 #include "bulk_copy.cuh"
 #include "ekf_math.cuh"
 
+#ifndef EKF_DEBUG_SKIP_RANK2
+#define EKF_DEBUG_SKIP_RANK2 0
+#endif
+
 namespace ekf {
 
 enum FusedMode : int { kDoPredict = 1, kDoMeasurement = 2, kDoAssociation = 4 };
@@ -101,35 +105,46 @@ __device__ __forceinline__ void warp_correct(double* __restrict__ sig, double* _
     }
     __syncwarp();
     if (lane == 0) st[0] = normalize_angle(st[0]);  // :187
-    // Sigma <- (I - K Hj) Sigma = Sigma - K W   (:191-192), in place in shared memory
-    {
+    // Sigma <- (I - K Hj) Sigma = Sigma - K W   (:191-192), in place in shared memory.
+    // Lane tiling 2 row groups x 16 column groups: lane (g, q) owns rows g, g+2, ... and columns q, q+16, q+32, ...
+    // Its W pairs stay in registers for the whole update and each K pair is fetched once per row (half as many
+    // operand fetches per element as a one-column-per-lane walk).  N is odd, so a half-warp (fixed g, q = 0..15)
+    // always hits 16 distinct 8-byte bank slots: conflict-free for every map size.
+    if (!EKF_DEBUG_SKIP_RANK2) {
         constexpr int NC = NL ? 3 + 2 * NL : 0;
-        const int main_cols = N < 32 ? N : 32;
-        if (lane < main_cols) {
-            const double2 w = W2[lane];
-            double* p = sig + lane;
-            if (NC) {
+        const int g = lane >> 4, q = lane & 15;
+        if (NC) {
+            constexpr int CB = (NC + 15) / 16;  // column slots per lane
+            constexpr int RA = (NC + 1) / 2;    // row slots per lane
+            double2 w[CB];
 #pragma unroll
-                for (int r = 0; r < NC; ++r) {
+            for (int b = 0; b < CB; ++b) w[b] = (q + 16 * b < NC) ? W2[q + 16 * b] : make_double2(0.0, 0.0);
+#pragma unroll
+            for (int a = 0; a < RA; ++a) {
+                const int r = g + 2 * a;
+                if (r < NC) {
                     const double2 k = K2[r];
-                    p[r * NC] = fma(-k.y, w.y, fma(-k.x, w.x, p[r * NC]));
-                }
-            } else {
-                for (int r = 0; r < N; ++r) {
-                    const double2 k = K2[r];
-                    p[r * N] = fma(-k.y, w.y, fma(-k.x, w.x, p[r * N]));
+                    double* row = sig + r * NC + q;
+#pragma unroll
+                    for (int b = 0; b < CB; ++b)
+                        if (q + 16 * b < NC) row[16 * b] = fma(-k.y, w[b].y, fma(-k.x, w[b].x, row[16 * b]));
                 }
             }
-        }
-        const int rc = N - 32;  // remainder columns [32, N)
-        if (rc > 0) {
-            const int total = N * rc;
-            for (int e = lane; e < total; e += 32) {
-                const int r = e / rc, c = 32 + (e - r * rc);
-                const double2 k = K2[r];
-                const double2 w = W2[c];
-                double* q = sig + r * N + c;
-                *q = fma(-k.y, w.y, fma(-k.x, w.x, *q));
+        } else {
+            for (int c0 = 0; c0 < N; c0 += 64) {  // four column slots per pass keep the generic path in registers
+                double2 w[4];
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    const int c = c0 + q + 16 * b;
+                    w[b] = c < N ? W2[c] : make_double2(0.0, 0.0);
+                }
+                for (int r = g; r < N; r += 2) {
+                    const double2 k = K2[r];
+                    double* row = sig + r * N + c0 + q;
+#pragma unroll
+                    for (int b = 0; b < 4; ++b)
+                        if (c0 + q + 16 * b < N) row[16 * b] = fma(-k.y, w[b].y, fma(-k.x, w[b].x, row[16 * b]));
+                }
             }
         }
     }
