@@ -67,14 +67,16 @@ struct FusedSmem {
 };
 
 // One landmark correction on the smem-resident filter (ekf_slam.cpp:138-192 == :335-390).
-// All lanes enter with identical (i, zr, zphi, theta, x, y).
+// All lanes enter with identical (i, h, zr, zphi).  `h` = H_j / z_hat of landmark i from the current state.
+// If i_next >= 0 the function returns H_j of landmark i_next, evaluated from the state AFTER this correction with
+// the pose (theta, x, y): that long scalar chain (sqrt, four divisions, atan2, two angle wraps) only depends on the
+// state update, so it is issued before the rank-2 update and overlaps its shared-memory traffic.
 template <int NL>
-__device__ __forceinline__ void warp_correct(double* __restrict__ sig, double* __restrict__ st,
-                                             double2* __restrict__ K2, double2* __restrict__ W2, const int N,
-                                             const int lane, const int i, const double zr, const double zphi,
-                                             const double theta, const double x, const double y) {
+__device__ __forceinline__ Hj warp_correct(double* __restrict__ sig, double* __restrict__ st,
+                                           double2* __restrict__ K2, double2* __restrict__ W2, const int N,
+                                           const int lane, const int i, const Hj h, const double zr, const double zphi,
+                                           const int i_next, const double theta, const double x, const double y) {
     const int i3 = 3 + 2 * i, i4 = i3 + 1;
-    const Hj h = make_hj(st[i3], st[i4], theta, x, y);
 
     // W = Hj * Sigma (2 x N, from 5 rows) and P = Sigma * Hj^T (N x 2, from 5 columns)
     for (int c = lane; c < N; c += 32) {
@@ -105,6 +107,8 @@ __device__ __forceinline__ void warp_correct(double* __restrict__ sig, double* _
     }
     __syncwarp();
     if (lane == 0) st[0] = normalize_angle(st[0]);  // :187
+    Hj h_next = h;
+    if (i_next >= 0) h_next = make_hj(st[3 + 2 * i_next], st[4 + 2 * i_next], theta, x, y);
     // Sigma <- (I - K Hj) Sigma = Sigma - K W   (:191-192), in place in shared memory.
     // Lane tiling 2 row groups x 16 column groups: lane (g, q) owns rows g, g+2, ... and columns q, q+16, q+32, ...
     // Its W pairs stay in registers for the whole update and each K pair is fetched once per row (half as many
@@ -149,6 +153,7 @@ __device__ __forceinline__ void warp_correct(double* __restrict__ sig, double* _
         }
     }
     __syncwarp();
+    return h_next;
 }
 
 template <int NL>
@@ -259,10 +264,15 @@ __global__ void __launch_bounds__(32) ekf_fused_kernel(const FusedParams p) {
             const int i_l = base + lane;
             const unsigned mask = __ballot_sync(0xffffffffu, i_l < n && vis[i_l] != 0);
             unsigned rem = mask;
+            Hj h;
+            bool have_h = false;
             while (rem) {
                 const int i = base + __ffs(rem) - 1;
                 rem &= rem - 1;
-                warp_correct<NL>(sig, st, K2, W2, N, lane, i, zbuf[2 * i], zbuf[2 * i + 1], theta, x, y);
+                if (!have_h) h = make_hj(st[3 + 2 * i], st[4 + 2 * i], theta, x, y);
+                const int i_next = rem ? base + __ffs(rem) - 1 : -1;
+                h = warp_correct<NL>(sig, st, K2, W2, N, lane, i, h, zbuf[2 * i], zbuf[2 * i + 1], i_next, theta, x, y);
+                have_h = i_next >= 0;
                 ++n_corr;
             }
         }
@@ -343,7 +353,9 @@ __global__ void __launch_bounds__(32) ekf_fused_kernel(const FusedParams p) {
             }
             int assoc = -1;
             if (min_d < kGateUpdate) {  // :330
-                warp_correct<NL>(sig, st, K2, W2, N, lane, min_idx, zr, zphi, st[0], st[1], st[2]);
+                const double th_l = st[0], x_l = st[1], y_l = st[2];  // live pose (:331-333)
+                const Hj h = make_hj(st[3 + 2 * min_idx], st[4 + 2 * min_idx], th_l, x_l, y_l);
+                warp_correct<NL>(sig, st, K2, W2, N, lane, min_idx, h, zr, zphi, -1, th_l, x_l, y_l);
                 ++n_corr;
                 assoc = min_idx;
             }
