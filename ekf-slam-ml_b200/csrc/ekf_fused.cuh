@@ -118,8 +118,8 @@ __device__ __forceinline__ Hj warp_correct(double* __restrict__ sig, double* __r
         constexpr int NC = NL ? 3 + 2 * NL : 0;
         const int g = lane >> 4, q = lane & 15;
         if (NC) {
-            constexpr int CB = (NC + 15) / 16;  // column slots per lane
-            constexpr int RA = (NC + 1) / 2;    // row slots per lane
+            constexpr int CB = NC ? (NC + 15) / 16 : 1;  // column slots per lane
+            constexpr int RA = NC ? (NC + 1) / 2 : 1;    // row slots per lane
             double2 w[CB];
 #pragma unroll
             for (int b = 0; b < CB; ++b) w[b] = (q + 16 * b < NC) ? W2[q + 16 * b] : make_double2(0.0, 0.0);
