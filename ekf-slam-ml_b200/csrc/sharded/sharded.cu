@@ -15,7 +15,7 @@
 #include <vector>
 
 #include "../../../include/ekf_sharded_b200.h"
-#include "../ekf_large.cuh"
+#include "../ekf_large_delayed.cuh"
 
 using namespace ekf;
 
@@ -122,23 +122,31 @@ __global__ void k_sh_ctx_h(const double* __restrict__ state, const double* __res
     ctx->zphi = zphi;
 }
 
-// partial W = Hj * Sigma restricted to the rows this shard owns (zeros stand in for the others)
+// partial W = Hj * Sigma_current restricted to the rows this shard owns (zeros stand in for the others).
+// Sigma_current = Sigma_0 - sum_{j<p} K_j W_j is rebuilt on the fly from the pending factors (ekf_large_delayed.cuh).
 __global__ void __launch_bounds__(256)
     k_sh_wpart(const double* __restrict__ sig_local, long long ld, long long r0, long long r1, int N,
-               const Ctx* __restrict__ ctx, double2* __restrict__ Wpart) {
+               const Ctx* __restrict__ ctx, const double2* __restrict__ Kp, const double2* __restrict__ Wp, int p,
+               double2* __restrict__ Wpart) {
     const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= ld) return;
-    if (!ctx->active) return;
     double2 w = make_double2(0.0, 0.0);
-    if (c < N) {
+    if (c < N && ctx->active) {
         const long long id[5] = {0, 1, 2, ctx->i3, ctx->i3 + 1};
         double s[5];
 #pragma unroll
-        for (int k = 0; k < 5; ++k) s[k] = (id[k] >= r0 && id[k] < r1) ? sig_local[(id[k] - r0) * ld + c] : 0.0;
+        for (int k = 0; k < 5; ++k) {
+            double v = 0.0;
+            if (id[k] >= r0 && id[k] < r1) {
+                v = sig_local[(id[k] - r0) * ld + c];
+                for (int j = 0; j < p; ++j) v = apply_factor(v, Kp[(long long)j * ld + id[k]], Wp[(long long)j * ld + c]);
+            }
+            s[k] = v;
+        }
         const Hj h = ctx->h;
         w = make_double2(h_row0(h, s[1], s[2], s[3], s[4]), h_row1(h, s[0], s[1], s[2], s[3], s[4]));
     }
-    Wpart[c] = w;
+    Wpart[c] = w;  // a dropped measurement contributes a zero factor
 }
 
 __global__ void k_sh_ctx_s(const double2* __restrict__ W2, Ctx* __restrict__ ctx) {
@@ -156,20 +164,33 @@ __global__ void k_sh_ctx_s(const double2* __restrict__ W2, Ctx* __restrict__ ctx
     ctx->nu1 = normalize_angle(__dsub_rn(ctx->zphi, h.zphi));
 }
 
-// K rows of this shard: K[r] = (Sigma[r, idx] Hj^T) S^-1
+// K rows of this shard: K[r] = (Sigma_current[r, idx] Hj^T) S^-1, written into factor slot p
 __global__ void __launch_bounds__(256)
     k_sh_gain(const double* __restrict__ sig_local, long long ld, long long r0, int rows, const Ctx* __restrict__ ctx,
-              double2* __restrict__ K2) {
+              double2* __restrict__ Kp, const double2* __restrict__ Wp, int p) {
     const int lr = blockIdx.x * blockDim.x + threadIdx.x;
     if (lr >= rows) return;
-    if (!ctx->active) return;
+    double2* Kout = Kp + (long long)p * ld;
+    if (!ctx->active) {
+        Kout[r0 + lr] = make_double2(0.0, 0.0);
+        return;
+    }
     const Hj h = ctx->h;
     const Sym2 si = ctx->si;
     const int i3 = ctx->i3;
     const double* row = sig_local + (long long)lr * ld;
-    const double q0 = row[0], q1 = row[1], q2 = row[2], q3 = row[i3], q4 = row[i3 + 1];
+    double q0 = row[0], q1 = row[1], q2 = row[2], q3 = row[i3], q4 = row[i3 + 1];
+    for (int j = 0; j < p; ++j) {
+        const double2 kj = Kp[(long long)j * ld + r0 + lr];
+        const double2* wj = Wp + (long long)j * ld;
+        q0 = apply_factor(q0, kj, wj[0]);
+        q1 = apply_factor(q1, kj, wj[1]);
+        q2 = apply_factor(q2, kj, wj[2]);
+        q3 = apply_factor(q3, kj, wj[i3]);
+        q4 = apply_factor(q4, kj, wj[i3 + 1]);
+    }
     const double p0 = h_row0(h, q1, q2, q3, q4), p1 = h_row1(h, q0, q1, q2, q3, q4);
-    K2[r0 + lr] = make_double2(fma(p1, si.i10, p0 * si.i00), fma(p1, si.i11, p0 * si.i01));
+    Kout[r0 + lr] = make_double2(fma(p1, si.i10, p0 * si.i00), fma(p1, si.i11, p0 * si.i01));
 }
 
 // every replica applies the same state update from the gathered K
@@ -330,6 +351,7 @@ struct ekf_sharded {
     ncclComm_t comm = nullptr;
     cudaStream_t stream = nullptr;
     int init_flag_host = 0;
+    int pending = 0;  // corrections whose factors are not yet applied to Sigma
     int m_cap = 0;
     const double2** d_srcs = nullptr;  // local mode: device array of Wpart pointers
     uint64_t launches = 0;
@@ -373,8 +395,8 @@ int alloc_shard(ekf_sharded* h, Shard& s, int rank) {
     const size_t ld = (size_t)h->ld;
     CU(cudaMalloc(&s.sig, sizeof(double) * std::max<size_t>(1, (size_t)s.rows) * ld));
     CU(cudaMalloc(&s.state, sizeof(double) * ld));
-    CU(cudaMalloc(&s.K2, sizeof(double2) * ld));
-    CU(cudaMalloc(&s.W2, sizeof(double2) * ld));
+    CU(cudaMalloc(&s.K2, sizeof(double2) * ld * kMaxPending));  // pending factor slots [kMaxPending][ld]
+    CU(cudaMalloc(&s.W2, sizeof(double2) * ld * kMaxPending));
     CU(cudaMalloc(&s.Wpart, sizeof(double2) * ld));
     if (rank == 0) {
         s.robot = s.sig;
@@ -397,8 +419,8 @@ int alloc_shard(ekf_sharded* h, Shard& s, int rank) {
     CU(cudaMalloc(&s.nupd, sizeof(unsigned long long)));
     CU(cudaMemsetAsync(s.sig, 0, sizeof(double) * std::max<size_t>(1, (size_t)s.rows) * ld, h->stream));
     CU(cudaMemsetAsync(s.state, 0, sizeof(double) * ld, h->stream));
-    CU(cudaMemsetAsync(s.K2, 0, sizeof(double2) * ld, h->stream));
-    CU(cudaMemsetAsync(s.W2, 0, sizeof(double2) * ld, h->stream));
+    CU(cudaMemsetAsync(s.K2, 0, sizeof(double2) * ld * kMaxPending, h->stream));
+    CU(cudaMemsetAsync(s.W2, 0, sizeof(double2) * ld * kMaxPending, h->stream));
     CU(cudaMemsetAsync(s.Wpart, 0, sizeof(double2) * ld, h->stream));
     CU(cudaMemsetAsync(s.ctx, 0, sizeof(Ctx), h->stream));
     CU(cudaMemsetAsync(s.cmd, 0, sizeof(UpdateCmd), h->stream));
@@ -448,29 +470,32 @@ int exchange_W(ekf_sharded* h) {
     if (h->local) {
         const int g = (int)((h->ld + 255) / 256);
         for (auto& s : h->sh) {
-            k_sum_shards<<<g, 256, 0, h->stream>>>(s.W2, h->d_srcs, h->world, h->ld);
+            k_sum_shards<<<g, 256, 0, h->stream>>>(s.W2 + (long long)h->pending * h->ld, h->d_srcs, h->world, h->ld);
             h->launches++;
         }
         CU(cudaGetLastError());
     } else {
         Shard& s = h->sh[0];
-        NC(ncclAllReduce(s.Wpart, s.W2, 2 * (size_t)h->ld, ncclDouble, ncclSum, h->comm, h->stream));
+        NC(ncclAllReduce(s.Wpart, s.W2 + (long long)h->pending * h->ld, 2 * (size_t)h->ld, ncclDouble, ncclSum, h->comm,
+                         h->stream));
     }
     return 0;
 }
 int exchange_K(ekf_sharded* h) {
+    const long long off = (long long)h->pending * h->ld;  // factor slot being filled
     if (h->local) {
         for (auto& src : h->sh)
             for (auto& dst : h->sh)
                 if (&src != &dst && src.rows > 0)
-                    CU(cudaMemcpyAsync(dst.K2 + src.r0, src.K2 + src.r0, sizeof(double2) * src.rows, cudaMemcpyDeviceToDevice,
-                                       h->stream));
+                    CU(cudaMemcpyAsync(dst.K2 + off + src.r0, src.K2 + off + src.r0, sizeof(double2) * src.rows,
+                                       cudaMemcpyDeviceToDevice, h->stream));
     } else {
         Shard& s = h->sh[0];
         NC(ncclGroupStart());
         for (int g = 0; g < h->world; ++g) {
             const long long r0 = h->r0_of[g], rows = h->r1_of[g] - r0;
-            if (rows > 0) NC(ncclBroadcast(s.K2 + r0, s.K2 + r0, 2 * (size_t)rows, ncclDouble, g, h->comm, h->stream));
+            if (rows > 0)
+                NC(ncclBroadcast(s.K2 + off + r0, s.K2 + off + r0, 2 * (size_t)rows, ncclDouble, g, h->comm, h->stream));
         }
         NC(ncclGroupEnd());
     }
@@ -504,33 +529,47 @@ int sweep_grid(const ekf_sharded* h, const Shard& s) {
     return (int)std::max(1LL, std::min(chunks * row_blocks, (long long)h->sm_count * 8));
 }
 
-// one landmark correction across all shards
+// apply the pending factors to every shard's own rows in one sweep
+int flush(ekf_sharded* h, int n_counted, bool use_cmd) {
+    if (h->pending == 0) return 0;
+    for (auto& s : h->sh) {
+        if (s.rows > 0) {
+            CU(launch_sweep_p(h->pending, s.sig, h->ld, s.rows, s.K2, s.W2, s.r0, s.nupd, n_counted, use_cmd ? s.cmd : nullptr,
+                              h->sm_count, h->stream));
+            h->launches++;
+        }
+    }
+    h->pending = 0;
+    return 0;
+}
+
+// one landmark correction across all shards: fills factor slot `pending`; Sigma is swept later (flush)
 int correct(ekf_sharded* h, bool use_cmd, bool stale_pose, int lm, double sx, double sy) {
     const int gl = (int)((h->ld + 255) / 256);
+    const int p = h->pending;
     for (auto& s : h->sh) {
         k_sh_ctx_h<<<1, 32, 0, h->stream>>>(s.state, stale_pose ? s.pose0 : s.state, use_cmd ? s.cmd : nullptr, lm, sx, sy, s.ctx);
-        k_sh_wpart<<<gl, 256, 0, h->stream>>>(s.sig, h->ld, s.r0, s.r1, h->N, s.ctx, s.Wpart);
+        k_sh_wpart<<<gl, 256, 0, h->stream>>>(s.sig, h->ld, s.r0, s.r1, h->N, s.ctx, s.K2, s.W2, p, s.Wpart);
         h->launches += 2;
     }
     CU(cudaGetLastError());
     int rc = exchange_W(h);
     if (rc) return rc;
     for (auto& s : h->sh) {
-        k_sh_ctx_s<<<1, 32, 0, h->stream>>>(s.W2, s.ctx);
-        if (s.rows > 0) k_sh_gain<<<(s.rows + 255) / 256, 256, 0, h->stream>>>(s.sig, h->ld, s.r0, s.rows, s.ctx, s.K2);
+        k_sh_ctx_s<<<1, 32, 0, h->stream>>>(s.W2 + (long long)p * h->ld, s.ctx);
+        if (s.rows > 0) k_sh_gain<<<(s.rows + 255) / 256, 256, 0, h->stream>>>(s.sig, h->ld, s.r0, s.rows, s.ctx, s.K2, s.W2, p);
         h->launches += 2;
     }
     CU(cudaGetLastError());
     rc = exchange_K(h);
     if (rc) return rc;
     for (auto& s : h->sh) {
-        k_sh_state<<<(h->N + 255) / 256, 256, 0, h->stream>>>(s.state, s.K2, s.ctx, h->N);
-        if (s.rows > 0)
-            k_large_sweep<<<sweep_grid(h, s), kSweepThreads, 0, h->stream>>>(s.sig, h->ld, s.rows, s.K2 + s.r0, s.W2,
-                                                                            use_cmd ? s.cmd : nullptr, nullptr, nullptr, s.nupd);
-        h->launches += 2;
+        k_sh_state<<<(h->N + 255) / 256, 256, 0, h->stream>>>(s.state, s.K2 + (long long)p * h->ld, s.ctx, h->N);
+        h->launches += 1;
     }
     CU(cudaGetLastError());
+    h->pending += 1;
+    if (h->pending == kMaxPending) return flush(h, use_cmd ? 0 : kMaxPending, false);
     return 0;
 }
 
@@ -728,7 +767,7 @@ int ekf_sharded_measurement(ekf_sharded* h, const double* xy, const uint8_t* vis
         int rc = correct(h, false, true, i, xy[2 * i], xy[2 * i + 1]);
         if (rc) return rc;
     }
-    return 0;
+    return flush(h, h->pending, false);
 }
 
 int ekf_sharded_data_association(ekf_sharded* h, const double* xy, int m, uint8_t* known, int32_t* assoc_out,
@@ -768,6 +807,8 @@ int ekf_sharded_data_association(ekf_sharded* h, const double* xy, int m, uint8_
         }
         CU(cudaGetLastError());
         rc = correct(h, true, false, 0, 0.0, 0.0);
+        if (rc) return rc;
+        rc = flush(h, 1, true);  // the next measurement's distances need the corrected Sigma
         if (rc) return rc;
     }
     Shard& s0 = h->sh[0];  // every replica holds the same decisions
