@@ -180,7 +180,6 @@ struct ekf_filter {
     double* d_motion = nullptr;
     double* d_pose0 = nullptr;
     UpdateCmd* d_cmd = nullptr;
-    Special5* d_sp = nullptr;
     AssocPartial* d_partials = nullptr;
     unsigned int* d_done = nullptr;
     int* d_known_count = nullptr;
@@ -214,7 +213,6 @@ int free_filter(ekf_filter* h) {
     cudaFree(h->d_motion);
     cudaFree(h->d_pose0);
     cudaFree(h->d_cmd);
-    cudaFree(h->d_sp);
     cudaFree(h->d_partials);
     cudaFree(h->d_done);
     cudaFree(h->d_known_count);
@@ -304,14 +302,6 @@ FusedParams fused_params(ekf_filter* h, int mode, int m_max) {
     p.sig_stride = (int)h->sig_elems;
     p.st_stride = h->st_stride;
     return p;
-}
-
-int sweep_grid(const ekf_filter* h) {
-    const long long chunks = (h->ld + kSweepChunk - 1) / kSweepChunk;
-    const long long row_blocks = (h->N + kSweepRows - 1) / kSweepRows;
-    const long long tiles = chunks * row_blocks;
-    const long long cap = (long long)h->sm_count * 8;
-    return (int)std::max(1LL, std::min(tiles, cap));
 }
 
 // Apply the pending factors to Sigma in one sweep (ekf_large_delayed.cuh).
@@ -432,13 +422,11 @@ int ekf_create_ex(int n, int device, int engine, ekf_filter** out) {
         CUH(cudaMalloc(&h->d_motion, 2 * sizeof(double)));
         CUH(cudaMalloc(&h->d_pose0, 3 * sizeof(double)));
         CUH(cudaMalloc(&h->d_cmd, sizeof(UpdateCmd)));
-        CUH(cudaMalloc(&h->d_sp, sizeof(Special5)));
         h->assoc_blocks = std::max(1, std::min((n + 255) / 256, 1024));
         CUH(cudaMalloc(&h->d_partials, sizeof(AssocPartial) * h->assoc_blocks));
         CUH(cudaMalloc(&h->d_done, sizeof(unsigned int)));
         CUH(cudaMalloc(&h->d_known_count, sizeof(int)));
         CUH(cudaMemsetAsync(h->d_done, 0, sizeof(unsigned int), h->stream));
-        CUH(cudaMemsetAsync(h->d_sp, 0, sizeof(Special5), h->stream));
         CUH(cudaMemsetAsync(h->d_cmd, 0, sizeof(UpdateCmd), h->stream));
         CUH(cudaMemsetAsync(h->d_K2, 0, sizeof(double2) * (size_t)h->ld * kMaxPending, h->stream));
         CUH(cudaMemsetAsync(h->d_W2, 0, sizeof(double2) * (size_t)h->ld * kMaxPending, h->stream));

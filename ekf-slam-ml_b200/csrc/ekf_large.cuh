@@ -3,7 +3,8 @@
 // padded to a multiple of 16 doubles (128 B) so that every row starts on a cache line and 256-bit
 // loads/stores are aligned.  Per landmark correction the work is
 //   gain  : O(N)  — 5 rows + 5 columns of Sigma -> W = Hj Sigma (2 x N), K = Sigma Hj^T S^-1 (N x 2), state
-//   sweep : O(N^2)— Sigma -= K W, streamed once through the SMs: one HBM read + one HBM write of Sigma.
+//   sweep : O(N^2)— Sigma -= sum K W, streamed once through the SMs: one HBM read + one HBM write of Sigma
+// (both kernels live in ekf_large_delayed.cuh; this header holds prediction, association and shared pieces).
 // Restates rigid2d/src/ekf_slam.cpp:55-106, :108-197, :200-214, :217-276, :278-402.
 #pragma once
 #include "ekf_math.cuh"
@@ -17,14 +18,6 @@ struct UpdateCmd {
     int created;    // a new landmark was initialised for this measurement
     int pad;
     double sx, sy;
-};
-
-// New values of the five state entries that H_j depends on.  The gain kernel must not overwrite them while
-// other CTAs still read the old ones, so they are parked here and committed by the sweep kernel.
-struct Special5 {
-    double v[5];
-    int idx[5];
-    int valid;
 };
 
 struct AssocPartial {
@@ -189,99 +182,7 @@ __global__ void __launch_bounds__(256)
     if (created_out) created_out[j] = (uint8_t)created;
 }
 
-// ---------------------------------------------------------------- gain (ekf_slam.cpp:138-187 / 331-385)
-// grid covers k in [0, ld): thread k produces W[:,k] (from the 5 rows), K[k,:] (from the 5 columns of row k)
-// and the new state[k].  Every CTA first recomputes the O(1) part (Hj, S^-1, innovation) from the 5x5 block.
-struct GainShared {
-    Hj h;
-    Sym2 si;
-    double nu0, nu1;
-    int i3;
-    int active;
-};
-
-__global__ void __launch_bounds__(256)
-    k_large_gain(const double* __restrict__ sig, long long ld, int N, double* __restrict__ state,
-                 const double* __restrict__ pose_src, const UpdateCmd* __restrict__ cmd, int lm_arg, double sx_arg,
-                 double sy_arg, double2* __restrict__ K2, double2* __restrict__ W2, Special5* __restrict__ sp) {
-    __shared__ GainShared g;
-    if (threadIdx.x == 0) {
-        int lm = lm_arg;
-        double sx = sx_arg, sy = sy_arg;
-        int active = 1;
-        if (cmd) {
-            active = cmd->do_update;
-            lm = cmd->lm;
-            sx = cmd->sx;
-            sy = cmd->sy;
-        }
-        g.active = active;
-        if (active) {
-            const int i3 = 3 + 2 * lm;
-            const double theta = pose_src[0], x = pose_src[1], y = pose_src[2];
-            const Hj h = make_hj(state[i3], state[i3 + 1], theta, x, y);
-            const long long id[5] = {0, 1, 2, i3, i3 + 1};
-            double w0[5], w1[5];
-            for (int l = 0; l < 5; ++l) {
-                const double s0 = sig[id[0] * ld + id[l]], s1 = sig[id[1] * ld + id[l]], s2 = sig[id[2] * ld + id[l]];
-                const double s3 = sig[id[3] * ld + id[l]], s4 = sig[id[4] * ld + id[l]];
-                w0[l] = h_row0(h, s1, s2, s3, s4);
-                w1[l] = h_row1(h, s0, s1, s2, s3, s4);
-            }
-            const double s00 = h_row0(h, w0[1], w0[2], w0[3], w0[4]) + kR;
-            const double s01 = h_row1(h, w0[0], w0[1], w0[2], w0[3], w0[4]);
-            const double s10 = h_row0(h, w1[1], w1[2], w1[3], w1[4]);
-            const double s11 = h_row1(h, w1[0], w1[1], w1[2], w1[3], w1[4]) + kR;
-            g.h = h;
-            g.si = inv2x2(s00, s01, s10, s11);
-            double zr, zphi;
-            range_bearing(sx, sy, zr, zphi);
-            g.nu0 = __dsub_rn(zr, h.zr);
-            g.nu1 = normalize_angle(__dsub_rn(zphi, h.zphi));
-            g.i3 = i3;
-        }
-    }
-    __syncthreads();
-    if (!g.active) return;
-    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= ld) return;
-    if (k >= N) {  // padding columns/rows stay inert in the sweep
-        K2[k] = make_double2(0.0, 0.0);
-        W2[k] = make_double2(0.0, 0.0);
-        return;
-    }
-    const Hj h = g.h;
-    const int i3 = g.i3, i4 = i3 + 1;
-    {
-        const double s0 = sig[k], s1 = sig[ld + k], s2 = sig[2 * ld + k];
-        const double s3 = sig[i3 * ld + k], s4 = sig[i4 * ld + k];
-        W2[k] = make_double2(h_row0(h, s1, s2, s3, s4), h_row1(h, s0, s1, s2, s3, s4));
-    }
-    const double* row = sig + k * ld;
-    const double r0 = row[0], r1 = row[1], r2 = row[2], r3 = row[i3], r4 = row[i4];
-    const double p0 = h_row0(h, r1, r2, r3, r4), p1 = h_row1(h, r0, r1, r2, r3, r4);
-    const double k0 = fma(p1, g.si.i10, p0 * g.si.i00);
-    const double k1 = fma(p1, g.si.i11, p0 * g.si.i01);
-    K2[k] = make_double2(k0, k1);
-    double ns = state[k] + fma(k1, g.nu1, k0 * g.nu0);
-    int slot = -1;
-    if (k < 3)
-        slot = (int)k;
-    else if (k == i3)
-        slot = 3;
-    else if (k == i4)
-        slot = 4;
-    if (slot < 0) {
-        state[k] = ns;
-    } else {
-        if (k == 0) ns = normalize_angle(ns);  // ekf_slam.cpp:187
-        sp->v[slot] = ns;
-        sp->idx[slot] = (int)k;
-        if (k == 0) sp->valid = 1;
-    }
-}
-
-// ---------------------------------------------------------------- sweep (ekf_slam.cpp:191-192 / 389-390)
+// ---------------------------------------------------------------- 256-bit global accesses (LDG/STG.E.256 on sm_100a)
 __device__ __forceinline__ void ld256(const double* p, double& a, double& b, double& c, double& d) {
     asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
 }
@@ -290,67 +191,7 @@ __device__ __forceinline__ void st256(double* p, double a, double b, double c, d
 }
 
 constexpr int kSweepThreads = 256;
-constexpr int kSweepColsPerThread = 4;
-constexpr int kSweepChunk = kSweepThreads * kSweepColsPerThread;  // 1024 columns = 8 KB of a row
-constexpr int kSweepRows = 32;                                    // rows per tile
-
-// Sigma[r][c] -= K[r][0] W[0][c] + K[r][1] W[1][c], streamed.  A tile is kSweepRows x kSweepChunk doubles
-// (256 KB); each thread keeps its four columns of W in registers for the whole tile and moves 32 B per row
-// with one 256-bit load and one 256-bit store.  Tiles are walked by a grid-stride loop so the grid can be
-// sized to a multiple of the SM count.
-__global__ void __launch_bounds__(kSweepThreads)
-    k_large_sweep(double* __restrict__ sig, long long ld, int N, const double2* __restrict__ K2,
-                  const double2* __restrict__ W2, const UpdateCmd* __restrict__ cmd, Special5* __restrict__ sp,
-                  double* __restrict__ state, unsigned long long* __restrict__ n_updates) {
-    if (cmd && !cmd->do_update) return;
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-        if (sp && sp->valid) {
-            for (int s = 0; s < 5; ++s) state[sp->idx[s]] = sp->v[s];
-            sp->valid = 0;
-        }
-        if (n_updates) *n_updates += 1;
-    }
-    const int chunks = (int)((ld + kSweepChunk - 1) / kSweepChunk);
-    const int row_blocks = (N + kSweepRows - 1) / kSweepRows;
-    const long long tiles = (long long)chunks * row_blocks;
-    for (long long t = blockIdx.x; t < tiles; t += gridDim.x) {
-        const int rb = (int)(t / chunks), cc = (int)(t - (long long)rb * chunks);
-        const long long c = (long long)cc * kSweepChunk + threadIdx.x * kSweepColsPerThread;
-        if (c >= ld) continue;
-        const double2 w0 = W2[c], w1 = W2[c + 1], w2 = W2[c + 2], w3 = W2[c + 3];
-        const int r_begin = rb * kSweepRows;
-        const int r_end = min(N, r_begin + kSweepRows);
-        double* p = sig + (long long)r_begin * ld + c;
-        int r = r_begin;
-        for (; r + 4 <= r_end; r += 4) {
-            double v[4][4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) ld256(p + u * ld, v[u][0], v[u][1], v[u][2], v[u][3]);
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const double2 k = K2[r + u];
-                v[u][0] = fma(-k.y, w0.y, fma(-k.x, w0.x, v[u][0]));
-                v[u][1] = fma(-k.y, w1.y, fma(-k.x, w1.x, v[u][1]));
-                v[u][2] = fma(-k.y, w2.y, fma(-k.x, w2.x, v[u][2]));
-                v[u][3] = fma(-k.y, w3.y, fma(-k.x, w3.x, v[u][3]));
-            }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) st256(p + u * ld, v[u][0], v[u][1], v[u][2], v[u][3]);
-            p += 4 * ld;
-        }
-        for (; r < r_end; ++r) {
-            double a, b, cdd, d;
-            ld256(p, a, b, cdd, d);
-            const double2 k = K2[r];
-            a = fma(-k.y, w0.y, fma(-k.x, w0.x, a));
-            b = fma(-k.y, w1.y, fma(-k.x, w1.x, b));
-            cdd = fma(-k.y, w2.y, fma(-k.x, w2.x, cdd));
-            d = fma(-k.y, w3.y, fma(-k.x, w3.x, d));
-            st256(p, a, b, cdd, d);
-            p += ld;
-        }
-    }
-}
+constexpr int kSweepRows = 32;
 
 // Sigma0 = blockdiag(0_3, 100 I) (ekf_slam.cpp:29-36) on an already-zeroed buffer.
 __global__ void k_large_init_sigma(double* __restrict__ sig, long long ld, int N) {

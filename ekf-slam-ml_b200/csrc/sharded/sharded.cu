@@ -523,12 +523,6 @@ int exchange_partials(ekf_sharded* h) {
     return 0;
 }
 
-int sweep_grid(const ekf_sharded* h, const Shard& s) {
-    const long long chunks = (h->ld + kSweepChunk - 1) / kSweepChunk;
-    const long long row_blocks = (s.rows + kSweepRows - 1) / kSweepRows;
-    return (int)std::max(1LL, std::min(chunks * row_blocks, (long long)h->sm_count * 8));
-}
-
 // apply the pending factors to every shard's own rows in one sweep
 int flush(ekf_sharded* h, int n_counted, bool use_cmd) {
     if (h->pending == 0) return 0;
