@@ -123,15 +123,33 @@ __device__ __forceinline__ Hj warp_correct(double* __restrict__ sig, double* __r
             double2 w[CB];
 #pragma unroll
             for (int b = 0; b < CB; ++b) w[b] = (q + 16 * b < NC) ? W2[q + 16 * b] : make_double2(0.0, 0.0);
+            // Rows go through in batches of RB: all shared-memory loads of a batch are issued before its FMAs and
+            // stores, so one load latency is paid per batch instead of per row (ptxas keeps program order between
+            // the stores of one row and the loads of the next).
+            constexpr int RB = 6;
 #pragma unroll
-            for (int a = 0; a < RA; ++a) {
-                const int r = g + 2 * a;
-                if (r < NC) {
-                    const double2 k = K2[r];
-                    double* row = sig + r * NC + q;
+            for (int a0 = 0; a0 < RA; a0 += RB) {
+                double2 k[RB];
+                double v[RB][CB];
 #pragma unroll
-                    for (int b = 0; b < CB; ++b)
-                        if (q + 16 * b < NC) row[16 * b] = fma(-k.y, w[b].y, fma(-k.x, w[b].x, row[16 * b]));
+                for (int u = 0; u < RB; ++u) {
+                    const int r = g + 2 * (a0 + u);
+                    if (a0 + u < RA && r < NC) {
+                        k[u] = K2[r];
+#pragma unroll
+                        for (int b = 0; b < CB; ++b)
+                            if (q + 16 * b < NC) v[u][b] = sig[r * NC + q + 16 * b];
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < RB; ++u) {
+                    const int r = g + 2 * (a0 + u);
+                    if (a0 + u < RA && r < NC) {
+#pragma unroll
+                        for (int b = 0; b < CB; ++b)
+                            if (q + 16 * b < NC)
+                                sig[r * NC + q + 16 * b] = fma(-k[u].y, w[b].y, fma(-k[u].x, w[b].x, v[u][b]));
+                    }
                 }
             }
         } else {
