@@ -252,7 +252,7 @@ def sharded_map_leg(pkg, dist, local, n_lm, timed_updates, peak_gbs):
     tr = tg.simulate_known(w, 1, steps, seed=77)
     f = ShardedEKF.from_process_group(n_lm, dist, local)
     N = 3 + 2 * n_lm
-    done, t, total_ms = 0, 0, 0.0
+    done, t, total_ms, n_sweeps = 0, 0, 0.0, 0
     l0 = None
     while t < steps and done < timed_updates:
         nvis = int(tr["vis"][t, 0].sum())
@@ -268,6 +268,7 @@ def sharded_map_leg(pkg, dist, local, n_lm, timed_updates, peak_gbs):
         if timed and nvis:
             total_ms += pkg.sharding.allreduce_max(f.timer_stop(), dist, "cuda")
             done += nvis
+            n_sweeps += -(-nvis // 8)
         t += 1
     ms_upd = total_ms / max(done, 1)
     rows = f.rows(0)
@@ -277,11 +278,77 @@ def sharded_map_leg(pkg, dist, local, n_lm, timed_updates, peak_gbs):
                     f"{world} GPUs; per correction: NCCL all-reduce of W (2N fp64) + all-gather of K (2N fp64), sweep of own rows",
         "value": 1e3 / ms_upd, "unit": UNIT, "updates_timed": done, "ms_per_update": ms_upd,
         "gpu_launches_rank0": int(f.launch_count - (l0 or 0)), "rows_rank0": list(rows),
-        "roofline": {"bound": "hbm", "achieved": per_gpu_bytes / (ms_upd * 1e-3) / 1e9, "peak": peak_gbs, "unit": "GB/s per GPU",
-                     "frac": per_gpu_bytes / (ms_upd * 1e-3) / 1e9 / peak_gbs, "traffic": None,
-                     "algorithmic_bytes_per_update_per_gpu": per_gpu_bytes},
+        "roofline": {"bound": "hbm", "kernel": "k_large_sweep_p<P> on each rank's rows (time per sweep = whole step incl. "
+                                                "prediction, gains and the NCCL exchanges)",
+                     "achieved": per_gpu_bytes * n_sweeps / (total_ms * 1e-3) / 1e9, "peak": peak_gbs, "unit": "GB/s per GPU",
+                     "frac": per_gpu_bytes * n_sweeps / (total_ms * 1e-3) / 1e9 / peak_gbs, "traffic": None,
+                     "algorithmic_bytes_per_launch_per_gpu": per_gpu_bytes, "sweeps": n_sweeps,
+                     "updates_per_sweep": done / max(n_sweeps, 1),
+                     "per_update_achieved": per_gpu_bytes / (ms_upd * 1e-3) / 1e9,
+                     "per_update_frac": per_gpu_bytes / (ms_upd * 1e-3) / 1e9 / peak_gbs},
     }
     f.close()
+    return out
+
+
+def laser_leg(pkg, device, n_scans=8192):
+    """(d) of the north star: 360-beam scans -> clusters -> circle fits -> classification, batched over scans."""
+    import torch
+    tg = pkg.tracegen
+    sim = tg.TubeWorldSim(tg.default_world(), n_scans // 2, seed=31)
+    scans = []
+    for _ in range(2):
+        for _ in range(21):
+            sim.step_tick()
+        scans.append(sim.laser_scan(360))
+    scans = np.ascontiguousarray(np.concatenate(scans, axis=0))
+    cf = pkg.CircleFitting(device=device, max_scans=n_scans, max_circles=16)
+    centers, counts = cf.run_batch(scans)          # warm-up through the host path
+    t0 = time.perf_counter()
+    reps = 5
+    for _ in range(reps):
+        centers, counts = cf.run_batch(scans)
+    e2e = reps * n_scans / (time.perf_counter() - t0)
+    L = pkg._lib.load()
+    d_scans = torch.from_numpy(scans).cuda()
+    pkg.circle_fitting._check(L.circles_run_dev_f32(cf._ctx, d_scans.data_ptr(), n_scans))
+    pkg.circle_fitting._check(L.circles_sync(cf._ctx))
+    pkg.circle_fitting._check(L.circles_timer_start(cf._ctx))
+    for _ in range(reps):
+        pkg.circle_fitting._check(L.circles_run_dev_f32(cf._ctx, d_scans.data_ptr(), n_scans))
+    ms = ctypes.c_float()
+    pkg.circle_fitting._check(L.circles_timer_stop(cf._ctx, ctypes.byref(ms)))
+    return {"workload": f"{n_scans} scans x 360 beams (float32), default 10-tube world: clustering + circle fit + classification",
+            "scans_per_s_device": reps * n_scans / (ms.value * 1e-3), "scans_per_s_e2e": e2e,
+            "circles_per_scan": float(counts.mean()), "kernel": "k_circles_scan<float>", "gpu_launches": reps}
+
+
+def batch_unknown_leg(pkg, device, B, steps, warmup):
+    """cfg3, unknown-association variant: prediction + data_association (Mahalanobis gating) per filter and step."""
+    import torch
+    tg = pkg.tracegen
+    M = 12
+    T = steps + warmup
+    tr = tg.simulate_unknown(tg.dense_world(N_SLOTS), B, T, seed=4242, m_max=M)
+    bt = pkg.EKFBatch(B, N_SLOTS, device=device)
+    d_tw = torch.from_numpy(np.ascontiguousarray(tr["twists"])).cuda()
+    d_me = torch.from_numpy(np.ascontiguousarray(tr["meas"])).cuda()
+    d_ct = torch.from_numpy(np.ascontiguousarray(tr["count"])).cuda()
+    torch.cuda.synchronize()
+    for t in range(warmup):
+        bt.step_unknown_dev(d_tw[t].data_ptr(), d_me[t].data_ptr(), d_ct[t].data_ptr(), M)
+    bt.sync()
+    u0 = bt.update_count
+    bt.timer_start()
+    for t in range(warmup, T):
+        bt.step_unknown_dev(d_tw[t].data_ptr(), d_me[t].data_ptr(), d_ct[t].data_ptr(), M)
+    ms = bt.timer_stop()
+    upd = bt.update_count - u0
+    meas = int(tr["count"][warmup:].sum())
+    out = {"workload": f"cfg3 unknown association: {B} filters x 20 slots, up to {M} unlabelled measurements per step",
+           "value": upd / (ms * 1e-3), "unit": UNIT, "measurements_per_s": meas / (ms * 1e-3), "ms_per_step": ms / steps,
+           "updates_per_step": upd / steps, "gpu_launches": steps}
+    bt.close()
     return out
 
 
@@ -440,6 +507,8 @@ def run_ours(args):
             del d_tw, d_xy, d_vis
             torch.cuda.empty_cache()
             line["large_map"] = large_map_leg(pkg, local, args.large_n, args.large_updates, peak_gbs, want_cpu=True)
+            line["batch_unknown"] = batch_unknown_leg(pkg, local, B, K, W)
+            line["laser"] = laser_leg(pkg, local)
     if world > 1 and not args.skip_large:
         # cfg5 needs every rank: free the batch first (Sigma shard = 51.2 GB / world per GPU)
         bt.close()

@@ -53,6 +53,7 @@ SIGNATURES = {
     "ekf_device_pointers": (ctypes.c_int, [ctypes.c_void_p, c_void_pp, c_i64_p, c_void_pp]),
     "ekf_stream": (ctypes.c_void_p, [ctypes.c_void_p]),
     "ekf_launch_count": (ctypes.c_int, [ctypes.c_void_p, c_u64_p]),
+    "ekf_set_max_pending": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     "ekf_batch_create": (ctypes.c_int, [ctypes.c_int64, ctypes.c_int, ctypes.c_int, c_void_pp]),
     "ekf_batch_destroy": (ctypes.c_int, [ctypes.c_void_p]),
     "ekf_batch_size": (ctypes.c_int64, [ctypes.c_void_p]),

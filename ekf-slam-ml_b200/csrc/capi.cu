@@ -177,6 +177,7 @@ struct ekf_filter {
     double2* d_W2 = nullptr;  // [kMaxPending][ld] pending H*Sigma factors
     double* d_state_alt = nullptr;  // ping-pong partner of d_state (the gain kernel never writes what it reads)
     int pending = 0;                // corrections computed but not yet applied to Sigma
+    int max_pending = kMaxPending;  // flush threshold (1 = the reference's one sweep per correction)
     double* d_motion = nullptr;
     double* d_pose0 = nullptr;
     UpdateCmd* d_cmd = nullptr;
@@ -324,7 +325,7 @@ int stream_correct(ekf_filter* h, const double* pose_src, const UpdateCmd* cmd, 
     CU(cudaGetLastError());
     std::swap(h->d_state, h->d_state_alt);
     h->pending += 1;
-    if (h->pending == kMaxPending) return stream_flush(h, cmd ? 0 : kMaxPending, nullptr);
+    if (h->pending >= h->max_pending) return stream_flush(h, cmd ? 0 : h->pending, nullptr);
     return EKF_OK;
 }
 
@@ -698,6 +699,13 @@ int ekf_device_pointers(ekf_filter* h, void** sigma, int64_t* ld, void** state) 
     if (sigma) *sigma = h->d_sigma;
     if (ld) *ld = h->ld;
     if (state) *state = h->d_state;
+    return EKF_OK;
+}
+// How many corrections the streamed engine may accumulate before it sweeps Sigma (1..8, default 8).  The result
+// is bit-identical for every setting; 1 reproduces the reference's schedule of one full pass per correction.
+int ekf_set_max_pending(ekf_filter* h, int max_pending) {
+    if (!h || max_pending < 1 || max_pending > kMaxPending) return fail(EKF_ERR_INVALID, "max_pending must be 1..%d", kMaxPending);
+    h->max_pending = max_pending;
     return EKF_OK;
 }
 int ekf_launch_count(ekf_filter* h, uint64_t* out) {

@@ -196,6 +196,10 @@ class EKF_SLAM:
     def sync(self):
         check(self._L.ekf_sync(self._h))
 
+    def set_max_pending(self, k):
+        """Streamed engine: corrections accumulated per pass over Sigma (1..8); results do not depend on it."""
+        check(self._L.ekf_set_max_pending(self._h, int(k)))
+
     def timer_start(self):
         check(self._L.ekf_timer_start(self._h))
 

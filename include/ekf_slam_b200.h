@@ -91,6 +91,9 @@ int ekf_get_init_flag(ekf_filter* h, int* out);  /* landmark_init_flag, ekf_slam
 int ekf_set_init_flag(ekf_filter* h, int v);
 int ekf_update_count(ekf_filter* h, uint64_t* out); /* landmark corrections executed so far */
 int ekf_sync(ekf_filter* h);
+/* Streamed engine only: corrections accumulated before Sigma is swept (1..8, default 8).  Results are bit-identical
+ * for every value; 1 reproduces the reference's schedule of one pass over Sigma per correction (ekf_slam.cpp:191-192). */
+int ekf_set_max_pending(ekf_filter* h, int max_pending);
 /* raw device pointers for callers that live on the GPU already (bench, fused pipelines) */
 int ekf_device_pointers(ekf_filter* h, void** sigma, int64_t* ld, void** state);
 void* ekf_stream(ekf_filter* h); /* cudaStream_t */

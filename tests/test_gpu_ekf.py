@@ -343,3 +343,25 @@ def test_scan_to_map_pipeline(gpu_pkg):
             n_meas += k
     assert n_meas > 100 and ko.sum() >= 5
     assert state_err(f.state, o.state) < 1e-8 and sigma_err(f.sigma, o.sigma) < 1e-8
+
+
+def test_delayed_application_is_bit_identical(gpu_pkg):
+    """Accumulating up to 8 corrections per pass over Sigma (ekf_large_delayed.cuh) must give exactly the bits of
+    the reference's schedule (one pass per correction): every element sees the same FMA sequence."""
+    n = 300
+    tg = gpu_pkg.tracegen
+    w = tg.grid_world(20, 15, pitch=0.4, n_slots=n, max_visible=1.2)
+    tr = tg.simulate_known(w, 1, 8, seed=21)
+    outs = []
+    for k in (1, 3, 8):
+        f = gpu_pkg.EKF_SLAM(n, engine=gpu_pkg.ENGINE_STREAM)
+        f.set_max_pending(k)
+        for t in range(8):
+            f.prediction(tuple(tr["twists"][t, 0]))
+            f.measurement(tr["xy"][t, 0], tr["vis"][t, 0])
+        outs.append((f.state, f.sigma, f.launch_count))
+    assert int(tr["vis"][1:].sum(axis=2).max()) > 8  # some steps need more than one group even at k = 8
+    for st, sg, _ in outs[1:]:
+        assert np.array_equal(st.view(np.uint64), outs[0][0].view(np.uint64))
+        assert np.array_equal(sg.view(np.uint64), outs[0][1].view(np.uint64))
+    assert outs[2][2] < outs[0][2]  # fewer launches: fewer sweeps
