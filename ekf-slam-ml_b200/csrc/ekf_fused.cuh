@@ -45,7 +45,7 @@ __host__ __device__ inline int fused_round16(int v) { return (v + 15) & ~15; }
 
 // shared memory carve-up (bytes), identical on host and device
 struct FusedSmem {
-    int off_sig, off_st, off_k2, off_w2, off_z, off_bar, total;
+    int off_sig, off_st, off_k2, off_w2, off_k2b, off_w2b, off_z, off_bar, total;
     __host__ __device__ FusedSmem(int n, int m_max) {
         const int N = 3 + 2 * n;
         int o = 0;
@@ -53,43 +53,70 @@ struct FusedSmem {
         o += fused_round16(N * N) * 8;
         off_st = o;
         o += fused_round16(N) * 8;
-        off_k2 = o;
-        o += fused_round16(2 * N) * 8;
+        off_k2 = o;  // factor A: K (N x 2) and W (2 x N) as double2 per row / column
+        o += N * 16;
         off_w2 = o;
-        o += fused_round16(2 * N) * 8;
+        o += N * 16;
+        off_k2b = o;  // factor B (second correction of a pair)
+        o += N * 16;
+        off_w2b = o;
+        o += N * 16;
+        o = (o + 15) & ~15;
         off_z = o;
         const int zc = 2 * (n > m_max ? n : m_max);
-        o += fused_round16(zc) * 8;
+        o += zc * 8;  // n = 20: 18,320 B per CTA in total, so that 12 CTAs (+1 KB reserve each) fit one SM's 227 KB
         off_bar = o;
         o += 16;
         total = o;
     }
 };
 
-// One landmark correction on the smem-resident filter (ekf_slam.cpp:138-192 == :335-390).
-// All lanes enter with identical (i, h, zr, zphi).  `h` = H_j / z_hat of landmark i from the current state.
-// If i_next >= 0 the function returns H_j of landmark i_next, evaluated from the state AFTER this correction with
-// the pose (theta, x, y): that long scalar chain (sqrt, four divisions, atan2, two angle wraps) only depends on the
-// state update, so it is issued before the rank-2 update and overlaps its shared-memory traffic.
-template <int NL>
-__device__ __forceinline__ Hj warp_correct(double* __restrict__ sig, double* __restrict__ st,
-                                           double2* __restrict__ K2, double2* __restrict__ W2, const int N,
-                                           const int lane, const int i, const Hj h, const double zr, const double zphi,
-                                           const int i_next, const double theta, const double x, const double y) {
-    const int i3 = 3 + 2 * i, i4 = i3 + 1;
+__device__ __forceinline__ double apply_pair(double v, double2 k, double2 w) {
+    return fma(-k.y, w.y, fma(-k.x, w.x, v));
+}
 
-    // W = Hj * Sigma (2 x N, from 5 rows) and P = Sigma * Hj^T (N x 2, from 5 columns)
+// Gain part of one landmark correction on the smem-resident filter (ekf_slam.cpp:138-187 == :335-385):
+// W = Hj Sigma (2 x N) -> Wout, K = Sigma Hj^T S^-1 (N x 2) -> Kout, state += K nu.  Sigma itself is NOT touched.
+// If PEND, Sigma in shared memory is still missing the factor pair (Kpend, Wpend) of the previous correction; the
+// five rows and five columns that this correction needs are rebuilt on the fly with exactly the FMAs the rank-2
+// update would have applied (so the result is bit-identical to updating Sigma after every correction).
+// All lanes enter with identical (i, h, zr, zphi); h = H_j / z_hat of landmark i from the current state.
+template <bool PEND>
+__device__ __forceinline__ void warp_gain(const double* __restrict__ sig, double* __restrict__ st,
+                                          const double2* __restrict__ Kpend, const double2* __restrict__ Wpend,
+                                          double2* __restrict__ Kout, double2* __restrict__ Wout, const int N,
+                                          const int lane, const int i, const Hj h, const double zr, const double zphi) {
+    const int i3 = 3 + 2 * i, i4 = i3 + 1;
+    double2 ka[5], wa[5];
+    if (PEND) {
+        ka[0] = Kpend[0], ka[1] = Kpend[1], ka[2] = Kpend[2], ka[3] = Kpend[i3], ka[4] = Kpend[i4];
+        wa[0] = Wpend[0], wa[1] = Wpend[1], wa[2] = Wpend[2], wa[3] = Wpend[i3], wa[4] = Wpend[i4];
+    }
+    // W = Hj * Sigma (from 5 rows) and P = Sigma * Hj^T (from 5 columns)
     for (int c = lane; c < N; c += 32) {
-        const double s0 = sig[c], s1 = sig[N + c], s2 = sig[2 * N + c];
-        const double s3 = sig[i3 * N + c], s4 = sig[i4 * N + c];
-        W2[c] = make_double2(h_row0(h, s1, s2, s3, s4), h_row1(h, s0, s1, s2, s3, s4));
+        double s0 = sig[c], s1 = sig[N + c], s2 = sig[2 * N + c];
+        double s3 = sig[i3 * N + c], s4 = sig[i4 * N + c];
         const double* row = sig + c * N;
-        const double r0 = row[0], r1 = row[1], r2 = row[2], r3 = row[i3], r4 = row[i4];
-        K2[c] = make_double2(h_row0(h, r1, r2, r3, r4), h_row1(h, r0, r1, r2, r3, r4));
+        double r0 = row[0], r1 = row[1], r2 = row[2], r3 = row[i3], r4 = row[i4];
+        if (PEND) {
+            const double2 wc = Wpend[c], kc = Kpend[c];
+            s0 = apply_pair(s0, ka[0], wc);
+            s1 = apply_pair(s1, ka[1], wc);
+            s2 = apply_pair(s2, ka[2], wc);
+            s3 = apply_pair(s3, ka[3], wc);
+            s4 = apply_pair(s4, ka[4], wc);
+            r0 = apply_pair(r0, kc, wa[0]);
+            r1 = apply_pair(r1, kc, wa[1]);
+            r2 = apply_pair(r2, kc, wa[2]);
+            r3 = apply_pair(r3, kc, wa[3]);
+            r4 = apply_pair(r4, kc, wa[4]);
+        }
+        Wout[c] = make_double2(h_row0(h, s1, s2, s3, s4), h_row1(h, s0, s1, s2, s3, s4));
+        Kout[c] = make_double2(h_row0(h, r1, r2, r3, r4), h_row1(h, r0, r1, r2, r3, r4));
     }
     __syncwarp();
     // S = (Hj Sigma) Hj^T + R from W at the five columns; closed-form inverse
-    const double2 w0 = W2[0], w1 = W2[1], w2 = W2[2], w3 = W2[i3], w4 = W2[i4];
+    const double2 w0 = Wout[0], w1 = Wout[1], w2 = Wout[2], w3 = Wout[i3], w4 = Wout[i4];
     const double s00 = h_row0(h, w1.x, w2.x, w3.x, w4.x) + kR;
     const double s01 = h_row1(h, w0.x, w1.x, w2.x, w3.x, w4.x);
     const double s10 = h_row0(h, w1.y, w2.y, w3.y, w4.y);
@@ -99,79 +126,94 @@ __device__ __forceinline__ Hj warp_correct(double* __restrict__ sig, double* __r
     const double nu1 = normalize_angle(__dsub_rn(zphi, h.zphi));  // :182-183
     // K = P S^-1; state += K nu
     for (int r = lane; r < N; r += 32) {
-        const double2 p = K2[r];
+        const double2 p = Kout[r];
         const double k0 = fma(p.y, si.i10, p.x * si.i00);
         const double k1 = fma(p.y, si.i11, p.x * si.i01);
-        K2[r] = make_double2(k0, k1);
+        Kout[r] = make_double2(k0, k1);
         st[r] = st[r] + fma(k1, nu1, k0 * nu0);
     }
     __syncwarp();
     if (lane == 0) st[0] = normalize_angle(st[0]);  // :187
-    Hj h_next = h;
-    if (i_next >= 0) h_next = make_hj(st[3 + 2 * i_next], st[4 + 2 * i_next], theta, x, y);
-    // Sigma <- (I - K Hj) Sigma = Sigma - K W   (:191-192), in place in shared memory.
-    // Lane tiling 2 row groups x 16 column groups: lane (g, q) owns rows g, g+2, ... and columns q, q+16, q+32, ...
-    // Its W pairs stay in registers for the whole update and each K pair is fetched once per row (half as many
-    // operand fetches per element as a one-column-per-lane walk).  N is odd, so a half-warp (fixed g, q = 0..15)
-    // always hits 16 distinct 8-byte bank slots: conflict-free for every map size.
-    if (!EKF_DEBUG_SKIP_RANK2) {
-        constexpr int NC = NL ? 3 + 2 * NL : 0;
-        const int g = lane >> 4, q = lane & 15;
-        if (NC) {
-            constexpr int CB = NC ? (NC + 15) / 16 : 1;  // column slots per lane
-            constexpr int RA = NC ? (NC + 1) / 2 : 1;    // row slots per lane
-            double2 w[CB];
+    __syncwarp();
+}
+
+// Sigma <- Sigma - Ka Wa [- Kb Wb]   ((I - K Hj) Sigma, ekf_slam.cpp:191-192, for one or two corrections in ONE pass
+// over the shared-memory copy of Sigma; the factors are applied in order, two FMAs each, per element).
+// Lane tiling 2 row groups x 16 column groups: lane (g, q) owns rows g, g+2, ... and columns q, q+16, q+32, ...
+// Its W pairs stay in registers for the whole pass and each K pair is fetched once per row.  N is odd, so a
+// half-warp (fixed g, q = 0..15) always hits 16 distinct 8-byte bank slots: conflict-free for every map size.
+// Rows go through in batches of RB so that one shared-memory latency is paid per batch, not per row.
+template <int NL, int NF>
+__device__ __forceinline__ void warp_rank2(double* __restrict__ sig, const double2* __restrict__ Ka,
+                                           const double2* __restrict__ Wa, const double2* __restrict__ Kb,
+                                           const double2* __restrict__ Wb, const int N, const int lane) {
+    if (EKF_DEBUG_SKIP_RANK2) return;
+    constexpr int NC = NL ? 3 + 2 * NL : 0;
+    const int g = lane >> 4, q = lane & 15;
+    if (NC) {
+        constexpr int CB = NC ? (NC + 15) / 16 : 1;  // column slots per lane
+        constexpr int RA = NC ? (NC + 1) / 2 : 1;    // row slots per lane
+        constexpr int RB = (NF == 1) ? 6 : 4;
+        double2 wa[CB], wb[CB];
 #pragma unroll
-            for (int b = 0; b < CB; ++b) w[b] = (q + 16 * b < NC) ? W2[q + 16 * b] : make_double2(0.0, 0.0);
-            // Rows go through in batches of RB: all shared-memory loads of a batch are issued before its FMAs and
-            // stores, so one load latency is paid per batch instead of per row (ptxas keeps program order between
-            // the stores of one row and the loads of the next).
-            constexpr int RB = 6;
+        for (int b = 0; b < CB; ++b) {
+            wa[b] = (q + 16 * b < NC) ? Wa[q + 16 * b] : make_double2(0.0, 0.0);
+            if (NF == 2) wb[b] = (q + 16 * b < NC) ? Wb[q + 16 * b] : make_double2(0.0, 0.0);
+        }
 #pragma unroll
-            for (int a0 = 0; a0 < RA; a0 += RB) {
-                double2 k[RB];
-                double v[RB][CB];
+        for (int a0 = 0; a0 < RA; a0 += RB) {
+            double2 ka[RB], kb[RB];
+            double v[RB][CB];
 #pragma unroll
-                for (int u = 0; u < RB; ++u) {
-                    const int r = g + 2 * (a0 + u);
-                    if (a0 + u < RA && r < NC) {
-                        k[u] = K2[r];
+            for (int u = 0; u < RB; ++u) {
+                const int r = g + 2 * (a0 + u);
+                if (a0 + u < RA && r < NC) {
+                    ka[u] = Ka[r];
+                    if (NF == 2) kb[u] = Kb[r];
 #pragma unroll
-                        for (int b = 0; b < CB; ++b)
-                            if (q + 16 * b < NC) v[u][b] = sig[r * NC + q + 16 * b];
-                    }
-                }
-#pragma unroll
-                for (int u = 0; u < RB; ++u) {
-                    const int r = g + 2 * (a0 + u);
-                    if (a0 + u < RA && r < NC) {
-#pragma unroll
-                        for (int b = 0; b < CB; ++b)
-                            if (q + 16 * b < NC)
-                                sig[r * NC + q + 16 * b] = fma(-k[u].y, w[b].y, fma(-k[u].x, w[b].x, v[u][b]));
-                    }
+                    for (int b = 0; b < CB; ++b)
+                        if (q + 16 * b < NC) v[u][b] = sig[r * NC + q + 16 * b];
                 }
             }
-        } else {
-            for (int c0 = 0; c0 < N; c0 += 64) {  // four column slots per pass keep the generic path in registers
-                double2 w[4];
 #pragma unroll
-                for (int b = 0; b < 4; ++b) {
-                    const int c = c0 + q + 16 * b;
-                    w[b] = c < N ? W2[c] : make_double2(0.0, 0.0);
-                }
-                for (int r = g; r < N; r += 2) {
-                    const double2 k = K2[r];
-                    double* row = sig + r * N + c0 + q;
+            for (int u = 0; u < RB; ++u) {
+                const int r = g + 2 * (a0 + u);
+                if (a0 + u < RA && r < NC) {
 #pragma unroll
-                    for (int b = 0; b < 4; ++b)
-                        if (c0 + q + 16 * b < N) row[16 * b] = fma(-k.y, w[b].y, fma(-k.x, w[b].x, row[16 * b]));
+                    for (int b = 0; b < CB; ++b)
+                        if (q + 16 * b < NC) {
+                            double t = apply_pair(v[u][b], ka[u], wa[b]);
+                            if (NF == 2) t = apply_pair(t, kb[u], wb[b]);
+                            sig[r * NC + q + 16 * b] = t;
+                        }
                 }
+            }
+        }
+    } else {
+        for (int c0 = 0; c0 < N; c0 += 64) {  // four column slots per pass keep the generic path in registers
+            double2 wa[4], wb[4];
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                const int c = c0 + q + 16 * b;
+                wa[b] = c < N ? Wa[c] : make_double2(0.0, 0.0);
+                if (NF == 2) wb[b] = c < N ? Wb[c] : make_double2(0.0, 0.0);
+            }
+            for (int r = g; r < N; r += 2) {
+                const double2 ka = Ka[r];
+                double2 kb = make_double2(0.0, 0.0);
+                if (NF == 2) kb = Kb[r];
+                double* row = sig + r * N + c0 + q;
+#pragma unroll
+                for (int b = 0; b < 4; ++b)
+                    if (c0 + q + 16 * b < N) {
+                        double t = apply_pair(row[16 * b], ka, wa[b]);
+                        if (NF == 2) t = apply_pair(t, kb, wb[b]);
+                        row[16 * b] = t;
+                    }
             }
         }
     }
     __syncwarp();
-    return h_next;
 }
 
 template <int NL>
@@ -184,6 +226,8 @@ __global__ void __launch_bounds__(32) ekf_fused_kernel(const FusedParams p) {
     double* st = reinterpret_cast<double*>(smem_raw + L.off_st);
     double2* K2 = reinterpret_cast<double2*>(smem_raw + L.off_k2);
     double2* W2 = reinterpret_cast<double2*>(smem_raw + L.off_w2);
+    double2* K2b = reinterpret_cast<double2*>(smem_raw + L.off_k2b);
+    double2* W2b = reinterpret_cast<double2*>(smem_raw + L.off_w2b);
     double* zbuf = reinterpret_cast<double*>(smem_raw + L.off_z);
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + L.off_bar);
 
@@ -281,17 +325,36 @@ __global__ void __launch_bounds__(32) ekf_fused_kernel(const FusedParams p) {
         for (int base = 0; base < n; base += 32) {
             const int i_l = base + lane;
             const unsigned mask = __ballot_sync(0xffffffffu, i_l < n && vis[i_l] != 0);
+            // Visible landmarks go through in PAIRS: both gains are computed first (the second one sees the first
+            // one's factor as "pending"), then ONE pass over Sigma applies both rank-2 updates.  That halves the
+            // shared-memory traffic of the covariance update, which is what bounds this kernel.  H_j of the next
+            // landmark is always evaluated right after the state update it depends on and before the covariance pass,
+            // so the long scalar chain overlaps the pass's shared-memory latency.
             unsigned rem = mask;
             Hj h;
-            bool have_h = false;
+            if (rem) {
+                const int i0 = base + __ffs(rem) - 1;
+                h = make_hj(st[3 + 2 * i0], st[4 + 2 * i0], theta, x, y);
+            }
             while (rem) {
-                const int i = base + __ffs(rem) - 1;
+                const int ia = base + __ffs(rem) - 1;
                 rem &= rem - 1;
-                if (!have_h) h = make_hj(st[3 + 2 * i], st[4 + 2 * i], theta, x, y);
-                const int i_next = rem ? base + __ffs(rem) - 1 : -1;
-                h = warp_correct<NL>(sig, st, K2, W2, N, lane, i, h, zbuf[2 * i], zbuf[2 * i + 1], i_next, theta, x, y);
-                have_h = i_next >= 0;
+                warp_gain<false>(sig, st, nullptr, nullptr, K2, W2, N, lane, ia, h, zbuf[2 * ia], zbuf[2 * ia + 1]);
                 ++n_corr;
+                if (rem) {
+                    const int ib = base + __ffs(rem) - 1;
+                    rem &= rem - 1;
+                    h = make_hj(st[3 + 2 * ib], st[4 + 2 * ib], theta, x, y);
+                    warp_gain<true>(sig, st, K2, W2, K2b, W2b, N, lane, ib, h, zbuf[2 * ib], zbuf[2 * ib + 1]);
+                    ++n_corr;
+                    if (rem) {
+                        const int in = base + __ffs(rem) - 1;
+                        h = make_hj(st[3 + 2 * in], st[4 + 2 * in], theta, x, y);
+                    }
+                    warp_rank2<NL, 2>(sig, K2, W2, K2b, W2b, N, lane);
+                } else {
+                    warp_rank2<NL, 1>(sig, K2, W2, nullptr, nullptr, N, lane);
+                }
             }
         }
     }
@@ -373,7 +436,8 @@ __global__ void __launch_bounds__(32) ekf_fused_kernel(const FusedParams p) {
             if (min_d < kGateUpdate) {  // :330
                 const double th_l = st[0], x_l = st[1], y_l = st[2];  // live pose (:331-333)
                 const Hj h = make_hj(st[3 + 2 * min_idx], st[4 + 2 * min_idx], th_l, x_l, y_l);
-                warp_correct<NL>(sig, st, K2, W2, N, lane, min_idx, h, zr, zphi, -1, th_l, x_l, y_l);
+                warp_gain<false>(sig, st, nullptr, nullptr, K2, W2, N, lane, min_idx, h, zr, zphi);
+                warp_rank2<NL, 1>(sig, K2, W2, nullptr, nullptr, N, lane);  // the next distances need the new Sigma
                 ++n_corr;
                 assoc = min_idx;
             }
