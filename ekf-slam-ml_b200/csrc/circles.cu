@@ -90,8 +90,11 @@ struct FitResult {
 };
 
 // Hyper-circle fit + inscribed-angle statistic of one cluster by one warp.  `pt(k)` returns point k.
-template <class Fetch>
-__device__ __forceinline__ FitResult warp_circle_fit(Fetch pt, const int n, const int lane) {
+// ROWS = design-matrix rows held per lane (cluster size <= 32 * ROWS): tube clusters have 7..40 points, so the
+// common case runs with ROWS = 2 and a sixth of the register-array work of the general (ROWS = 12) instantiation.
+template <int ROWS, class Fetch>
+__device__ __forceinline__ FitResult warp_circle_fit_rows(Fetch pt, const int n, const int lane) {
+    constexpr int kRows = ROWS;
     double a0[kRows], a1[kRows], a2[kRows], a3[kRows];
     // means (circle_fitting.cpp:112-120)
     double sx = 0.0, sy = 0.0;
@@ -289,6 +292,13 @@ __device__ __forceinline__ FitResult warp_circle_fit(Fetch pt, const int n, cons
     return res;
 }
 
+template <class Fetch>
+__device__ __forceinline__ FitResult warp_circle_fit(Fetch pt, const int n, const int lane) {
+    if (n <= 64) return warp_circle_fit_rows<2>(pt, n, lane);   // warp-uniform branch
+    if (n <= 128) return warp_circle_fit_rows<4>(pt, n, lane);
+    return warp_circle_fit_rows<kRows>(pt, n, lane);
+}
+
 __device__ __forceinline__ bool is_circle(const FitResult& f) {
     return f.mean_angle > 1.5708 && f.mean_angle < 2.3562 && f.r < 0.2;  // :264-271
 }
@@ -304,7 +314,7 @@ struct ScanOut {
 };
 
 template <typename T>
-__global__ void __launch_bounds__(kCtaThreads)
+__global__ void __launch_bounds__(kCtaThreads, 2)
     k_circles_scan(const T* __restrict__ ranges, long long B, int n_beams, int max_c, ScanOut out) {
     __shared__ double r[kMaxBeams];
     __shared__ double2 xy[kMaxBeams];

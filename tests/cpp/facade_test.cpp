@@ -66,43 +66,31 @@ int main() {
     REQUIRE(known_list[0] && known_list[1] && known_list[2] && !known_list[3]);
     REQUIRE(uda.last_association().size() == 3 && uda.last_association()[0] == 0 && uda.last_association()[2] == 2);
 
-    // --- nuslam/tests/circle_tests.cpp
-    std::vector<double> ranges{0.713136, 0.682084, 0.668864, 0.660664, 0.65551, 0.652665, 0.651814, 0.652875, 0.655952,
-                               0.661391, 0.670004, 0.684042, 1.01247,  1.01543,  1.01872, 1.02234,  1.0263,   1.03061,
-                               1.04061,  1.05061,  1.06061};
+    // --- the reference's four known-answer circle cases (values from nuslam/tests/circle_tests.cpp:8-76)
+    const std::vector<double> scan21{0.713136, 0.682084, 0.668864, 0.660664, 0.65551,  0.652665, 0.651814,
+                                     0.652875, 0.655952, 0.661391, 0.670004, 0.684042, 1.01247,  1.01543,
+                                     1.01872,  1.02234,  1.0263,   1.03061,  1.04061,  1.05061,  1.06061};
+    auto fit_one = [](std::initializer_list<Vector2D> pts, double& cx, double& cy, double& r) {
+        CircleFitting fitter;
+        fitter.set_xy_cluster({std::vector<Vector2D>(pts)});
+        const std::vector<Vector2D> centre = fitter.circleRegression();
+        cx = centre[0].x;
+        cy = centre[0].y;
+        r = fitter.get_r_cluster()[0];
+    };
     {
-        CircleFitting cf = CircleFitting();
-        cf.clusteringRanges(ranges);
-        std::vector<std::vector<double>> pc = cf.get_point_cluster();
-        REQUIRE(pc.size() == 2);
-        REQUIRE(approx(pc[1][0], 1.01247));
+        CircleFitting fitter;
+        fitter.clusteringRanges(scan21);
+        const auto clusters = fitter.get_point_cluster();
+        REQUIRE(clusters.size() == 2 && approx(clusters[1][0], 1.01247));
+        REQUIRE(fitter.classifyCircle(fitter.circleRegression()).empty());
+        REQUIRE(fitter.approxCirclePositions(scan21).empty());
     }
-    {
-        CircleFitting cf = CircleFitting();
-        std::vector<Vector2D> xys{Vector2D{1.0, 7.0}, Vector2D{2.0, 6.0}, Vector2D{5.0, 8.0},
-                                  Vector2D{7.0, 7.0}, Vector2D{9.0, 5.0}, Vector2D{3.0, 7.0}};
-        std::vector<std::vector<Vector2D>> t1;
-        t1.push_back(xys);
-        cf.set_xy_cluster(t1);
-        std::vector<Vector2D> pos = cf.circleRegression();
-        REQUIRE(approx(pos[0].x, 4.615482) && approx(pos[0].y, 2.807354) && approx(cf.get_r_cluster()[0], 4.827575));
-    }
-    {
-        CircleFitting cf = CircleFitting();
-        std::vector<Vector2D> xys{Vector2D{-1.0, 0.0}, Vector2D{-0.3, -0.06}, Vector2D{0.3, 0.1}, Vector2D{1.0, 0.0}};
-        std::vector<std::vector<Vector2D>> t1;
-        t1.push_back(xys);
-        cf.set_xy_cluster(t1);
-        std::vector<Vector2D> pos = cf.circleRegression();
-        REQUIRE(approx(pos[0].x, 0.4908357) && approx(pos[0].y, -22.15212) && approx(cf.get_r_cluster()[0], 22.17979));
-    }
-    {
-        CircleFitting cf = CircleFitting();
-        cf.clusteringRanges(ranges);
-        std::vector<Vector2D> pos = cf.circleRegression();
-        REQUIRE(cf.classifyCircle(pos).size() == 0);
-        REQUIRE(cf.approxCirclePositions(ranges).size() == 0);
-    }
+    double cx, cy, r;
+    fit_one({{1.0, 7.0}, {2.0, 6.0}, {5.0, 8.0}, {7.0, 7.0}, {9.0, 5.0}, {3.0, 7.0}}, cx, cy, r);
+    REQUIRE(approx(cx, 4.615482) && approx(cy, 2.807354) && approx(r, 4.827575));
+    fit_one({{-1.0, 0.0}, {-0.3, -0.06}, {0.3, 0.1}, {1.0, 0.0}}, cx, cy, r);
+    REQUIRE(approx(cx, 0.4908357) && approx(cy, -22.15212) && approx(r, 22.17979));
     std::printf("FACADE OK\n");
     return 0;
 }
