@@ -214,7 +214,9 @@ def large_map_leg(pkg, device, n_lm, timed_updates, peak_gbs, want_cpu):
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "kernel": "k_large_sweep_p<P> (time per sweep = whole step incl. predict + gains)",
                      "achieved": alg_bytes * n_sweeps / (sweep_ms_total * 1e-3) / 1e9, "peak": peak_gbs, "unit": "GB/s",
-                     "frac": alg_bytes * n_sweeps / (sweep_ms_total * 1e-3) / 1e9 / peak_gbs, "traffic": None,
+                     "frac": alg_bytes * n_sweeps / (sweep_ms_total * 1e-3) / 1e9 / peak_gbs,
+                     # ncu capture profiles/r1_prof_sweep_r1_final_raw.csv: 2.157 GB read + 2.090 GB written per launch
+                     "traffic": 4.247e9 if n_lm == 8192 else None,
                      "algorithmic_bytes_per_launch": alg_bytes, "sweeps": n_sweeps,
                      "updates_per_sweep": done / max(n_sweeps, 1),
                      "per_update_achieved": alg_bytes / (ms_upd * 1e-3) / 1e9,
@@ -472,7 +474,9 @@ def run_ours(args):
         "bound": "hbm", "kernel": "ekf_fused_kernel<20>", "unit": "GB/s", "peak": peak_gbs, "peak_source": peak_src,
         "achieved": step_bytes / (kern_ms_avg * 1e-3) / 1e9,
         "frac": step_bytes / (kern_ms_avg * 1e-3) / 1e9 / peak_gbs,
-        "traffic": None,
+        # dram__bytes_read.sum + dram__bytes_write.sum per launch of this kernel at this batch size, from the committed
+        # ncu --set full capture (profiles/superseded/r1_prof_fused_r1_raw.csv: 1.022 GB + 0.942 GB); not re-measured here
+        "traffic": 1.964e9 if B == FILTERS_PER_GPU else None,
         "algorithmic_bytes_per_launch": step_bytes,
         "note": "unit = one filter-step (prediction + all of the step's corrections with Sigma resident on chip): "
                 "16 N^2 B = one HBM read + one HBM write of Sigma; per_update_* uses SURVEY.md's 16 N^2 per correction "

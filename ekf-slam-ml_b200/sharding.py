@@ -24,6 +24,15 @@ def row_blocks(N, world, align=1):
     return b
 
 
+def landmark_row_blocks(n_landmarks, world):
+    """The partition the row-sharded engine uses (csrc/sharded/sharded.cu::partition): rank g owns the two rows of each
+    landmark in [L_g, L_g+1) with ceil(n / world) landmarks per rank, and rank 0 additionally the three robot rows.
+    Returns world+1 row boundaries; boundaries other than 0 and N are odd, so a landmark's row pair is never split."""
+    per = -(-n_landmarks // world)
+    lm = [min(n_landmarks, g * per) for g in range(world + 1)]
+    return [0] + [3 + 2 * v for v in lm[1:]]
+
+
 def owner_of_row(row, bounds):
     """Rank that owns `row` under boundaries from row_blocks()."""
     return int(np.searchsorted(np.asarray(bounds), row, side="right") - 1)

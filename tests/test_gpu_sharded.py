@@ -36,6 +36,7 @@ def test_local_emulation_known_association(gpu_pkg, n, world):
     assert bounds[0][0] == 0 and bounds[-1][1] == f.N
     assert all(bounds[g][1] == bounds[g + 1][0] for g in range(world - 1))
     assert all(b[0] % 2 == 1 for b in bounds[1:])
+    assert [b[0] for b in bounds] + [f.N] == gpu_pkg.sharding.landmark_row_blocks(n, world)
     worst = 0.0
     for t in range(10):
         f.prediction(tuple(tr["twists"][t, 0]))

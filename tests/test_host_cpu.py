@@ -104,6 +104,19 @@ def test_row_block_partition(pkg):
             assert b[g] <= row < b[g + 1]
 
 
+def test_landmark_row_partition_matches_engine_contract(pkg):
+    sh = pkg.sharding
+    for n, G in ((40000, 8), (40000, 2), (20, 3), (61, 4), (8192, 8)):
+        b = sh.landmark_row_blocks(n, G)
+        N = 3 + 2 * n
+        assert b[0] == 0 and b[-1] == N and len(b) == G + 1
+        assert all(x < y for x, y in zip(b, b[1:]))
+        assert all(x % 2 == 1 for x in b[1:])          # landmark row pairs (3+2i, 4+2i) are never split
+        assert sh.owner_of_row(0, b) == 0 and sh.owner_of_row(2, b) == 0
+        for i in (0, n // 2, n - 1):
+            assert sh.owner_of_row(3 + 2 * i, b) == sh.owner_of_row(4 + 2 * i, b)
+
+
 WORKER = r'''
 import os, sys
 import numpy as np
