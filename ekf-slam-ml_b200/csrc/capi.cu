@@ -13,7 +13,7 @@
 #include "../../include/ekf_slam_b200.h"
 #include "ekf_fused.cuh"
 #include "ekf_large.cuh"
-#include "ekf_large_delayed.cuh"
+#include "ekf_large_tma.cuh"
 
 using namespace ekf;
 
@@ -308,7 +308,7 @@ FusedParams fused_params(ekf_filter* h, int mode, int m_max) {
 // Apply the pending factors to Sigma in one sweep (ekf_large_delayed.cuh).
 int stream_flush(ekf_filter* h, int n_counted, const UpdateCmd* cmd) {
     if (h->pending == 0) return EKF_OK;
-    CU(launch_sweep_p(h->pending, h->d_sigma, h->ld, h->N, h->d_K2, h->d_W2, 0, h->d_nupd, n_counted, cmd, h->sm_count,
+    CU(launch_sweep(h->pending, h->d_sigma, h->ld, h->N, h->d_K2, h->d_W2, 0, h->d_nupd, n_counted, cmd, h->sm_count,
                       h->stream));
     h->launches += 1;
     h->pending = 0;
@@ -416,8 +416,8 @@ int ekf_create_ex(int n, int device, int engine, ekf_filter** out) {
         CUH(cudaMemsetAsync(h->d_state, 0, sizeof(double) * h->st_stride, h->stream));
         CUH(cudaMemsetAsync(h->d_init_flag, 0, sizeof(int32_t), h->stream));
         k_large_init_sigma<<<(h->N + 255) / 256, 256, 0, h->stream>>>(h->d_sigma, h->ld, h->N);
-        CUH(cudaMalloc(&h->d_K2, sizeof(double2) * (size_t)h->ld * kMaxPending));
-        CUH(cudaMalloc(&h->d_W2, sizeof(double2) * (size_t)h->ld * kMaxPending));
+        CUH(cudaMalloc(&h->d_K2, sizeof(double2) * ((size_t)h->ld * kMaxPending + 16)));
+        CUH(cudaMalloc(&h->d_W2, sizeof(double2) * ((size_t)h->ld * kMaxPending + 16)));
         CUH(cudaMalloc(&h->d_state_alt, sizeof(double) * h->st_stride));
         CUH(cudaMemsetAsync(h->d_state_alt, 0, sizeof(double) * h->st_stride, h->stream));
         CUH(cudaMalloc(&h->d_motion, 2 * sizeof(double)));

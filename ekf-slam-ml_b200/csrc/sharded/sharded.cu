@@ -15,7 +15,7 @@
 #include <vector>
 
 #include "../../../include/ekf_sharded_b200.h"
-#include "../ekf_large_delayed.cuh"
+#include "../ekf_large_tma.cuh"
 
 using namespace ekf;
 
@@ -395,8 +395,8 @@ int alloc_shard(ekf_sharded* h, Shard& s, int rank) {
     const size_t ld = (size_t)h->ld;
     CU(cudaMalloc(&s.sig, sizeof(double) * std::max<size_t>(1, (size_t)s.rows) * ld));
     CU(cudaMalloc(&s.state, sizeof(double) * ld));
-    CU(cudaMalloc(&s.K2, sizeof(double2) * ld * kMaxPending));  // pending factor slots [kMaxPending][ld]
-    CU(cudaMalloc(&s.W2, sizeof(double2) * ld * kMaxPending));
+    CU(cudaMalloc(&s.K2, sizeof(double2) * (ld * kMaxPending + 16)));  // pending factor slots [kMaxPending][ld]
+    CU(cudaMalloc(&s.W2, sizeof(double2) * (ld * kMaxPending + 16)));
     CU(cudaMalloc(&s.Wpart, sizeof(double2) * ld));
     if (rank == 0) {
         s.robot = s.sig;
@@ -528,7 +528,7 @@ int flush(ekf_sharded* h, int n_counted, bool use_cmd) {
     if (h->pending == 0) return 0;
     for (auto& s : h->sh) {
         if (s.rows > 0) {
-            CU(launch_sweep_p(h->pending, s.sig, h->ld, s.rows, s.K2, s.W2, s.r0, s.nupd, n_counted, use_cmd ? s.cmd : nullptr,
+            CU(launch_sweep(h->pending, s.sig, h->ld, s.rows, s.K2, s.W2, s.r0, s.nupd, n_counted, use_cmd ? s.cmd : nullptr,
                               h->sm_count, h->stream));
             h->launches++;
         }

@@ -3,7 +3,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <vector>
-#include "ekf_large_tma.cuh"
+#include "../ekf-slam-ml_b200/csrc/ekf_large_tma.cuh"
 using namespace ekf;
 
 template <int P>
@@ -58,8 +58,8 @@ int main(int argc, char** argv) {
     cudaMalloc(&a, sizeof(double) * ld * N);
     cudaMalloc(&b, sizeof(double) * ld * N);
     cudaMalloc(&init, sizeof(double) * ld * N);
-    cudaMalloc(&Kp, sizeof(double2) * ld * kMaxPending);
-    cudaMalloc(&Wp, sizeof(double2) * ld * kMaxPending);
+    cudaMalloc(&Kp, sizeof(double2) * (ld * kMaxPending + 16));
+    cudaMalloc(&Wp, sizeof(double2) * (ld * kMaxPending + 16));
     std::vector<double> h((size_t)ld * N);
     for (auto& v : h) v = rand() / (double)RAND_MAX;
     cudaMemcpy(init, h.data(), sizeof(double) * ld * N, cudaMemcpyHostToDevice);
