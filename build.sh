@@ -6,8 +6,8 @@ set -euo pipefail
 cd "$(dirname "$0")"
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 SRC=ekf-slam-ml_b200/csrc
-FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -Xcompiler -fvisibility=default"
-newest=$(ls -t $SRC/*.cu $SRC/*.cuh $SRC/sharded/*.cu include/*.h build.sh | head -1)
+FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -Xcompiler -fno-gnu-unique -Xlinker --version-script=$SRC/exports.map"
+newest=$(ls -t $SRC/*.cu $SRC/*.cuh $SRC/sharded/*.cu $SRC/exports.map include/*.h build.sh | head -1)
 
 OUT=ekf-slam-ml_b200/libekfslam_b200.so
 if [ -f "$OUT" ] && [ "$OUT" -nt "$newest" ] && [ "${FORCE:-0}" != "1" ]; then
