@@ -130,10 +130,10 @@ __device__ __forceinline__ void warp_gain(const double* __restrict__ sig, double
         const double k0 = fma(p.y, si.i10, p.x * si.i00);
         const double k1 = fma(p.y, si.i11, p.x * si.i01);
         Kout[r] = make_double2(k0, k1);
-        st[r] = st[r] + fma(k1, nu1, k0 * nu0);
+        double ns = st[r] + fma(k1, nu1, k0 * nu0);
+        if (r == 0) ns = normalize_angle(ns);  // theta is wrapped after every correction (:187)
+        st[r] = ns;
     }
-    __syncwarp();
-    if (lane == 0) st[0] = normalize_angle(st[0]);  // :187
     __syncwarp();
 }
 
