@@ -6,8 +6,9 @@ root-level shim:  ``import ekf_slam_ml_b200``.
 from . import _lib, sharding, tracegen
 from ._lib import EkfError, device_count
 from .circle_fitting import CircleFitting
+from .tube_world import TubeWorld
 from .ekf_slam import (EKF_SLAM, ENGINE_AUTO, ENGINE_FUSED, ENGINE_STREAM, EKFBatch, PinnedBuffer, Twist2D,
                        Vector2D, body_twist, normalize_angle)
 
 __all__ = ["EKF_SLAM", "EKFBatch", "PinnedBuffer", "Twist2D", "Vector2D", "body_twist", "normalize_angle",
-           "EkfError", "device_count", "tracegen", "sharding", "CircleFitting", "ENGINE_AUTO", "ENGINE_FUSED", "ENGINE_STREAM"]
+           "EkfError", "device_count", "tracegen", "sharding", "CircleFitting", "TubeWorld", "ENGINE_AUTO", "ENGINE_FUSED", "ENGINE_STREAM"]

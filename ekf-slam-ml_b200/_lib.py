@@ -98,6 +98,18 @@ SIGNATURES = {
     "circles_timer_start": (ctypes.c_int, [ctypes.c_void_p]),
     "circles_timer_stop": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_float)]),
     "circles_launch_count": (ctypes.c_int, [ctypes.c_void_p, c_u64_p]),
+    # include/tube_world_b200.h
+    "tubeworld_last_error": (ctypes.c_char_p, []),
+    "tubeworld_create": (ctypes.c_int, [ctypes.c_int64, ctypes.c_void_p, c_double_p, c_double_p, ctypes.c_int, ctypes.c_uint64,
+                                        ctypes.c_int64, ctypes.c_int, c_void_pp]),
+    "tubeworld_destroy": (ctypes.c_int, [ctypes.c_void_p]),
+    "tubeworld_step_known": (ctypes.c_int, [ctypes.c_void_p]),
+    "tubeworld_step_scan": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int]),
+    "tubeworld_outputs": (ctypes.c_int, [ctypes.c_void_p, c_void_pp, c_void_pp, c_void_pp, c_void_pp, c_void_pp]),
+    "tubeworld_download": (ctypes.c_int, [ctypes.c_void_p, c_double_p, c_double_p, c_u8_p, c_double_p, c_float_p]),
+    "tubeworld_sync": (ctypes.c_int, [ctypes.c_void_p]),
+    "tubeworld_stream": (ctypes.c_void_p, [ctypes.c_void_p]),
+    "tubeworld_set_stream": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
 }
 
 # include/ekf_sharded_b200.h (separate library: it links NCCL)

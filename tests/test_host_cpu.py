@@ -13,12 +13,12 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def declared_symbols():
     names = set()
-    for h in ("ekf_slam_b200.h", "circle_fit_b200.h", "ekf_sharded_b200.h"):
+    for h in ("ekf_slam_b200.h", "circle_fit_b200.h", "ekf_sharded_b200.h", "tube_world_b200.h"):
         p = os.path.join(ROOT, "include", h)
         if not os.path.exists(p):
             continue
         src = re.sub(r"/\*.*?\*/", "", open(p).read(), flags=re.S)
-        names |= set(re.findall(r"\b((?:ekf|circles)_[a-z0-9_]+)\s*\(", src))
+        names |= set(re.findall(r"\b((?:ekf|circles|tubeworld)_[a-z0-9_]+)\s*\(", src))
     return names
 
 
