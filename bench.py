@@ -354,6 +354,33 @@ def batch_unknown_leg(pkg, device, B, steps, warmup):
     return out
 
 
+def device_sim_leg(pkg, device, B, steps, warmup):
+    """simulator -> filter without leaving the GPU (tube_world restatement feeding the fused step)."""
+    tg = pkg.tracegen
+    sim = pkg.TubeWorld(tg.dense_world(N_SLOTS), B, seed=777, device=device)
+    bt = pkg.EKFBatch(B, N_SLOTS, device=device)
+    sim.use_stream(bt.stream)
+    p = sim.device_pointers()
+    for _ in range(warmup + 1):
+        sim.step_known()
+        bt.step_known_dev(p["twists"], p["xy"], p["vis"])
+    bt.sync()
+    u0 = bt.update_count
+    bt.timer_start()
+    for _ in range(steps):
+        sim.step_known()
+        bt.step_known_dev(p["twists"], p["xy"], p["vis"])
+    ms = bt.timer_stop()
+    upd = bt.update_count - u0
+    err = bt.pose_error(sim.download()["truth"])
+    out = {"workload": f"{B} robots simulated on the device (11 ticks + fake sensor per step) feeding the fused EKF step",
+           "value": upd / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / steps, "gpu_launches": 2 * steps,
+           "pose_rmse_xy": [float(np.sqrt(err[0] / err[3])), float(np.sqrt(err[1] / err[3]))]}
+    bt.close()
+    sim.close()
+    return out
+
+
 def run_ours(args):
     import ekf_slam_ml_b200 as pkg
     rank = int(os.environ.get("RANK", "0"))
@@ -513,6 +540,7 @@ def run_ours(args):
             line["large_map"] = large_map_leg(pkg, local, args.large_n, args.large_updates, peak_gbs, want_cpu=True)
             line["batch_unknown"] = batch_unknown_leg(pkg, local, B, K, W)
             line["laser"] = laser_leg(pkg, local)
+            line["device_sim"] = device_sim_leg(pkg, local, B, K, W)
     if world > 1 and not args.skip_large:
         # cfg5 needs every rank: free the batch first (Sigma shard = 51.2 GB / world per GPU)
         bt.close()
