@@ -376,8 +376,8 @@ def device_sim_leg(pkg, device, B, steps, warmup):
     out = {"workload": f"{B} robots simulated on the device (11 ticks + fake sensor per step) feeding the fused EKF step",
            "value": upd / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / steps, "gpu_launches": 2 * steps,
            "pose_rmse_xy": [float(np.sqrt(err[0] / err[3])), float(np.sqrt(err[1] / err[3]))]}
-    bt.close()
     sim.close()
+    bt.close()
     return out
 
 

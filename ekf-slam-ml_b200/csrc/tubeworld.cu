@@ -252,7 +252,9 @@ const char* tubeworld_last_error(void) { return tw::g_err; }
 int tubeworld_destroy(tubeworld* w) {
     if (!w) return 0;
     tw::Dev g(w->device);
-    if (w->stream) cudaStreamSynchronize(w->stream);
+    /* a borrowed stream may already be gone when the consumer was closed first: never touch it here */
+    if (w->stream && w->own_stream) cudaStreamSynchronize(w->stream);
+    else cudaDeviceSynchronize();
     cudaFree(w->d_tx);
     cudaFree(w->d_ty);
     cudaFree(w->d_robots);
