@@ -12,6 +12,7 @@
 
 #include "../../include/ekf_slam_b200.h"
 #include "ekf_fused.cuh"
+#include "ekf_fused_sym.cuh"
 #include "ekf_large.cuh"
 #include "ekf_large_tma.cuh"
 
@@ -59,8 +60,13 @@ int max_smem_optin(int device) {
 }
 
 // Launch the fused one-warp-per-filter kernel (n = 20 gets the fully unrolled instantiation).
+#ifndef EKF_DEBUG_EXTRA_SMEM
+#define EKF_DEBUG_EXTRA_SMEM 0  // occupancy experiments only
+#endif
+
 int launch_fused(const FusedParams& p, cudaStream_t stream, int device) {
-    const FusedSmem L(p.n, p.m_max);
+    FusedSmem L(p.n, p.m_max);
+    L.total += EKF_DEBUG_EXTRA_SMEM;
     if (L.total > max_smem_optin(device))
         return fail(EKF_ERR_UNSUPPORTED, "fused engine: %d B of shared memory needed for n=%d", L.total, p.n);
     if (p.B <= 0) return EKF_OK;
@@ -78,6 +84,36 @@ int launch_fused(const FusedParams& p, cudaStream_t stream, int device) {
             set0[device] = L.total;
         }
         ekf_fused_kernel<0><<<(unsigned)p.B, 32, L.total, stream>>>(p);
+    }
+    CU(cudaGetLastError());
+    return EKF_OK;
+}
+
+// Batched engine: symmetric staircase Sigma (ekf_fused_sym.cuh).
+int launch_fused_sym(const FusedParams& p, cudaStream_t stream, int device) {
+    SymSmem L(p.n, p.m_max);
+    if (L.total > max_smem_optin(device))
+        return fail(EKF_ERR_UNSUPPORTED, "fused engine: %d B of shared memory needed for n=%d", L.total, p.n);
+    if (p.B <= 0) return EKF_OK;
+    if (p.B > 0x7fffffffLL) return fail(EKF_ERR_INVALID, "batch too large for one launch");
+    L.total += EKF_DEBUG_EXTRA_SMEM;
+    static int set20[64] = {0}, set0[64] = {0};
+    if (p.n == 20) {
+        if (set20[device] < L.total) {
+            CU(cudaFuncSetAttribute(ekf_fused_sym_kernel<20>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
+            CU(cudaFuncSetAttribute(ekf_fused_sym_kernel<20>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                    cudaSharedmemCarveoutMaxShared));
+            set20[device] = L.total;
+        }
+        ekf_fused_sym_kernel<20><<<(unsigned)p.B, 32, L.total, stream>>>(p);
+    } else {
+        if (set0[device] < L.total) {
+            CU(cudaFuncSetAttribute(ekf_fused_sym_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
+            CU(cudaFuncSetAttribute(ekf_fused_sym_kernel<0>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                    cudaSharedmemCarveoutMaxShared));
+            set0[device] = L.total;
+        }
+        ekf_fused_sym_kernel<0><<<(unsigned)p.B, 32, L.total, stream>>>(p);
     }
     CU(cudaGetLastError());
     return EKF_OK;
@@ -744,7 +780,8 @@ struct ekf_batch {
     cudaStream_t copy_stream = nullptr;  // H2D of the next step's inputs
     cudaStream_t out_stream = nullptr;   // D2H of results
     uint64_t launches = 0;
-    double* d_sigma = nullptr;
+    double* d_sigma = nullptr;  // [B][sig_stride], symmetric staircase layout (ekf_fused_sym.cuh)
+    double* d_dense = nullptr;  // N x N scratch of ekf_batch_get_sigma
     double* d_state = nullptr;
     int32_t* d_init_flag = nullptr;
     uint8_t* d_known = nullptr;
@@ -774,6 +811,7 @@ int free_batch(ekf_batch* b) {
     DeviceGuard g(b->device);
     cudaDeviceSynchronize();
     cudaFree(b->d_sigma);
+    cudaFree(b->d_dense);
     cudaFree(b->d_state);
     cudaFree(b->d_init_flag);
     cudaFree(b->d_known);
@@ -862,8 +900,8 @@ int ekf_batch_create(int64_t B, int n, int device, ekf_batch** out) {
     b->n = n;
     b->N = 3 + 2 * n;
     b->device = device;
-    b->sig_stride = fused_round16(b->N * b->N);
-    b->st_stride = fused_round16(b->N);
+    b->sig_stride = sym_sig_stride(b->N);
+    b->st_stride = sym_st_stride(b->N);
 #define CUB(expr)                          \
     do {                                   \
         cudaError_t e_ = (expr);           \
@@ -900,8 +938,8 @@ int ekf_batch_create(int64_t B, int n, int device, ekf_batch** out) {
         free_batch(b);
         return fail(EKF_ERR_INVALID, "batch too large");
     }
-    k_fused_init<<<(unsigned)B, 128, 0, b->stream>>>(b->d_sigma, b->d_state, b->d_init_flag, B, b->N, b->sig_stride,
-                                                     b->st_stride);
+    k_fused_sym_init<<<(unsigned)B, 128, 0, b->stream>>>(b->d_sigma, b->d_state, b->d_init_flag, B, b->N,
+                                                         b->sig_stride, b->st_stride);
     b->launches += 1;
     CUB(cudaGetLastError());
     rc = batch_ensure_xy(b, n);
@@ -923,7 +961,7 @@ int ekf_batch_step_known_dev(ekf_batch* b, const double* d_twists, const double*
     if (!b || !d_twists || !d_xy || !d_visible) return fail(EKF_ERR_INVALID, "null argument");
     DeviceGuard g(b->device);
     FusedParams p = batch_params(b, kDoPredict | kDoMeasurement, 1, d_twists, d_xy, d_visible, nullptr, nullptr);
-    int rc = launch_fused(p, b->stream, b->device);
+    int rc = launch_fused_sym(p, b->stream, b->device);
     b->launches += 1;
     return rc;
 }
@@ -933,7 +971,7 @@ int ekf_batch_step_unknown_dev(ekf_batch* b, const double* d_twists, const doubl
     if (!b || !d_twists || !d_meas || m_max <= 0) return fail(EKF_ERR_INVALID, "invalid argument");
     DeviceGuard g(b->device);
     FusedParams p = batch_params(b, kDoPredict | kDoAssociation, m_max, d_twists, d_meas, nullptr, d_count, d_assoc_out);
-    int rc = launch_fused(p, b->stream, b->device);
+    int rc = launch_fused_sym(p, b->stream, b->device);
     b->launches += 1;
     return rc;
 }
@@ -1018,8 +1056,13 @@ int ekf_batch_get_states(ekf_batch* b, double* out) {
 int ekf_batch_get_sigma(ekf_batch* b, int64_t filter, double* out, int64_t ld) {
     if (!b || !out || filter < 0 || filter >= b->B || ld < b->N) return fail(EKF_ERR_INVALID, "invalid argument");
     DeviceGuard g(b->device);
-    CU(cudaMemcpy2DAsync(out, sizeof(double) * ld, b->d_sigma + (size_t)filter * b->sig_stride, sizeof(double) * b->N,
-                         sizeof(double) * b->N, b->N, cudaMemcpyDeviceToHost, b->stream));
+    // the batch keeps Sigma in the symmetric staircase layout; expand one filter's copy to dense N x N
+    if (!b->d_dense) CU(cudaMalloc(&b->d_dense, sizeof(double) * (size_t)b->N * b->N));
+    k_fused_sym_unpack<<<(b->N * b->N + 255) / 256, 256, 0, b->stream>>>(b->d_sigma + (size_t)filter * b->sig_stride,
+                                                                        b->d_dense, b->N);
+    CU(cudaGetLastError());
+    CU(cudaMemcpy2DAsync(out, sizeof(double) * ld, b->d_dense, sizeof(double) * b->N, sizeof(double) * b->N, b->N,
+                         cudaMemcpyDeviceToHost, b->stream));
     CU(cudaStreamSynchronize(b->stream));
     return EKF_OK;
 }

@@ -128,11 +128,77 @@ __device__ __forceinline__ Hj make_hj(double mx, double my, double theta, double
     return h;
 }
 
+// ---- innovation without an atan2 per correction (fused symmetric engine) -------------------------------------
+// The reference forms nu = [z_r - zhat_r, normalize(z_phi - zhat_phi)] from two atan2 results
+// (ekf_slam.cpp:140-146, :163-170, :182-183).  The wrapped bearing difference IS the angle between the measured
+// direction u = (sx, sy) / |s| and the predicted direction p = R(-theta) (dx, dy) / sqrt(d), both in the robot frame:
+//   sin(nu_phi) = p x u,  cos(nu_phi) = p . u.
+// Innovations are small (sensor noise + prediction error), so asin(sin(nu_phi)) from a short odd series is exact to
+// below one ulp for |sin| < 1/8; anything else (and a NaN) takes the reference's formulation, out of line.
+struct Reading {
+    double zr, ux, uy;  // range and unit direction of a robot-frame reading
+};
+__device__ __forceinline__ Reading make_reading(double sx, double sy) {
+    Reading z;
+    z.zr = sqrt(__dadd_rn(__dmul_rn(sx, sx), __dmul_rn(sy, sy)));
+    const double inv = 1.0 / z.zr;
+    z.ux = z.zr > 0.0 ? sx * inv : 1.0;  // atan2(0, 0) == 0
+    z.uy = z.zr > 0.0 ? sy * inv : 0.0;
+    return z;
+}
+
+static __device__ __noinline__ double bearing_innovation_reference(double dy, double dx, double theta, double uy, double ux) {
+    const double zhat_phi = normalize_angle(__dsub_rn(atan2(dy, dx), theta));
+    return normalize_angle(__dsub_rn(atan2(uy, ux), zhat_phi));
+}
+
+__device__ __forceinline__ double asin_small(double x) {  // |x| < 1/8: truncation error < 3e-19 relative
+    const double x2 = x * x;
+    double p = 12155.0 / 2490368.0;  // unused tail guard term keeps the last kept term's error negligible
+    p = fma(p, x2, 6435.0 / 557056.0);
+    p = fma(p, x2, 143.0 / 10240.0);
+    p = fma(p, x2, 231.0 / 13312.0);
+    p = fma(p, x2, 63.0 / 2816.0);
+    p = fma(p, x2, 35.0 / 1152.0);
+    p = fma(p, x2, 5.0 / 112.0);
+    p = fma(p, x2, 3.0 / 40.0);
+    p = fma(p, x2, 1.0 / 6.0);
+    return fma(x * x2, p, x);
+}
+
+struct Innov {
+    double a, b, e, f;  // H_j entries as in Hj
+    double nu0, nu1;
+};
+// (sth, cth) = sincos(theta) of the pose the reference linearises about.
+__device__ __forceinline__ Innov make_innov(double mx, double my, double theta, double sth, double cth, double x,
+                                            double y, const Reading z) {
+    Innov h;
+    const double dx = __dsub_rn(mx, x), dy = __dsub_rn(my, y);
+    const double d = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+    const double isq = rsqrt(d), sq = __dmul_rn(d, isq), id = __dmul_rn(isq, isq);
+    h.a = -__dmul_rn(dx, isq);
+    h.b = -__dmul_rn(dy, isq);
+    h.e = __dmul_rn(dy, id);
+    h.f = -__dmul_rn(dx, id);
+    h.nu0 = __dsub_rn(z.zr, sq);
+    const double px = fma(sth, dy, cth * dx), py = fma(cth, dy, -(sth * dx));
+    const double sn = fma(px, z.uy, -(py * z.ux)) * isq;
+    const double cs = fma(px, z.ux, py * z.uy);
+    if (cs > 0.0 && fabs(sn) < 0.125)
+        h.nu1 = asin_small(sn);
+    else
+        h.nu1 = bearing_innovation_reference(dy, dx, theta, z.uy, z.ux);
+    return h;
+}
+
 // Rows of H applied to five gathered values s0..s4 (values at indices 0,1,2,3+2i,4+2i).
-__device__ __forceinline__ double h_row0(const Hj& h, double s1, double s2, double s3, double s4) {
+template <class H>
+__device__ __forceinline__ double h_row0(const H& h, double s1, double s2, double s3, double s4) {
     return fma(-h.b, s4, fma(-h.a, s3, fma(h.b, s2, h.a * s1)));
 }
-__device__ __forceinline__ double h_row1(const Hj& h, double s0, double s1, double s2, double s3, double s4) {
+template <class H>
+__device__ __forceinline__ double h_row1(const H& h, double s0, double s1, double s2, double s3, double s4) {
     return fma(-h.f, s4, fma(-h.e, s3, fma(h.f, s2, fma(h.e, s1, -s0))));
 }
 
@@ -202,6 +268,7 @@ __device__ __forceinline__ double maha_distance(const double* __restrict__ sig, 
 // Motion model increments and Jacobian entries (ekf_slam.cpp:67-96): state[0..2] += u, A(1,0)=a1, A(2,0)=a2.
 struct Motion {
     double u0, u1, u2, a1, a2;
+    double s_new, c_new;  // sincos(theta + u0)
 };
 __device__ __forceinline__ Motion motion_model(double theta, double dtheta, double dx) {
     Motion m;
@@ -213,6 +280,8 @@ __device__ __forceinline__ Motion motion_model(double theta, double dtheta, doub
         m.u2 = __dmul_rn(dx, s);
         m.a1 = __dmul_rn(-dx, s);
         m.a2 = __dmul_rn(dx, c);
+        m.s_new = s;
+        m.c_new = c;
     } else {
         double s2, c2;
         sincos(__dadd_rn(theta, dtheta), &s2, &c2);
@@ -222,6 +291,8 @@ __device__ __forceinline__ Motion motion_model(double theta, double dtheta, doub
         m.u2 = __dsub_rn(__dmul_rn(q, c), __dmul_rn(q, c2));
         m.a1 = __dadd_rn(__dmul_rn(-q, c), __dmul_rn(q, c2));
         m.a2 = __dadd_rn(__dmul_rn(-q, s), __dmul_rn(q, s2));
+        m.s_new = s2;
+        m.c_new = c2;
     }
     return m;
 }
