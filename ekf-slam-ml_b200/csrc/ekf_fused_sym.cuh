@@ -18,6 +18,28 @@
 
 #include "ekf_fused.cuh"
 
+// rows per register batch of the rank-2 pass, by column chunks of the block row (3 / 2 / 1) and factors per pass.
+// Measured on B200 (65,536 x n = 20): anything that makes the kernel spill under the 128-register cap of 16 resident
+// filters per SM costs 15-20 %; batches of 2 rows (126 registers, no spills) are the fastest setting.
+#ifndef EKF_SYM_RB3_1
+#define EKF_SYM_RB3_1 2
+#endif
+#ifndef EKF_SYM_RB3_2
+#define EKF_SYM_RB3_2 2
+#endif
+#ifndef EKF_SYM_RB2_1
+#define EKF_SYM_RB2_1 2
+#endif
+#ifndef EKF_SYM_RB2_2
+#define EKF_SYM_RB2_2 2
+#endif
+#ifndef EKF_SYM_RB1
+#define EKF_SYM_RB1 2
+#endif
+#ifndef EKF_SYM_MINB
+#define EKF_SYM_MINB 16  // resident filters per SM the n = 20 kernel is compiled for
+#endif
+
 namespace ekf {
 
 // ---- staircase layout -------------------------------------------------------------------------------------------
@@ -141,7 +163,8 @@ __device__ __forceinline__ void sym_rank2_blockrow(double* __restrict__ sig, con
     constexpr int SL = (ROWS + 1) / 2;                               // row slots per lane group
     constexpr int LROW = NC - 16 * RBK;                              // row stride (odd)
     constexpr int BASE = stair_row_base(16 * RBK, NC);
-    constexpr int RB = (CH >= 3) ? 4 : (CH == 2 ? (NF == 1 ? 8 : 4) : 8);
+    constexpr int RB = (CH >= 3) ? (NF == 1 ? EKF_SYM_RB3_1 : EKF_SYM_RB3_2)
+                                 : (CH == 2 ? (NF == 1 ? EKF_SYM_RB2_1 : EKF_SYM_RB2_2) : EKF_SYM_RB1);
 #pragma unroll
     for (int a0 = 0; a0 < SL; a0 += RB) {
         double2 ka[RB], kb[RB];
@@ -256,7 +279,7 @@ __device__ __forceinline__ double sym_maha_distance(const double* __restrict__ s
 }
 
 template <int NL>
-__global__ void __launch_bounds__(32, NL == 20 ? 16 : 1) ekf_fused_sym_kernel(const FusedParams p) {
+__global__ void __launch_bounds__(32, NL == 20 ? EKF_SYM_MINB : 1) ekf_fused_sym_kernel(const FusedParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int n = NL ? NL : p.n;
     const int N = 3 + 2 * n;
@@ -301,7 +324,9 @@ __global__ void __launch_bounds__(32, NL == 20 ? 16 : 1) ekf_fused_sym_kernel(co
     }
     int init_flag = p.init_flag[b];
     int m = 0;
+    unsigned vis_reg = 0;  // visible flags of slots lane, lane + 32, ... (one bit each), fetched with the readings
     if (p.mode & kDoMeasurement) {
+        for (int i = lane, k = 0; i < n; i += 32, ++k) vis_reg |= (p.vis[b * n + i] != 0 ? 1u : 0u) << k;
         // range and unit direction of every slot's reading, lane-parallel (ekf_slam.cpp:140-146)
         for (int i = lane; i < n; i += 32) {
             const Reading z = make_reading(p.xy[b * 2 * n + 2 * i], p.xy[b * 2 * n + 2 * i + 1]);
@@ -371,10 +396,8 @@ __global__ void __launch_bounds__(32, NL == 20 ? 16 : 1) ekf_fused_sym_kernel(co
             __syncwarp();
         }
         if (!have_sincos) sincos(theta, &sth, &cth);
-        const uint8_t* vis = p.vis + b * n;
         for (int base = 0; base < n; base += 32) {
-            const int i_l = base + lane;
-            unsigned rem = __ballot_sync(0xffffffffu, i_l < n && vis[i_l] != 0);
+            unsigned rem = __ballot_sync(0xffffffffu, (vis_reg >> (base >> 5)) & 1u);
             // Visible landmarks go through in PAIRS: both gains first (the second sees the first one's factor as
             // pending), then ONE pass over Sigma applies both rank-2 updates.  H_j / nu of the next landmark are
             // evaluated right after the state update they depend on and before the pass, so the scalar chain
@@ -518,7 +541,7 @@ __global__ void __launch_bounds__(32, NL == 20 ? 16 : 1) ekf_fused_sym_kernel(co
         bulk_commit();
         p.init_flag[b] = init_flag;
         if (p.n_updates && n_corr) atomicAdd(p.n_updates, n_corr);
-        bulk_wait_all();
+        bulk_wait_read();  // shared memory must outlive the copy engine's reads; the writes drain with the grid
     }
 }
 
