@@ -791,7 +791,7 @@ struct ekf_batch {
     double* d_twists[2] = {nullptr, nullptr};
     double* d_xy[2] = {nullptr, nullptr};
     uint8_t* d_vis[2] = {nullptr, nullptr};
-    int32_t* d_count[2] = {nullptr, nullptr};
+    int32_t* d_count[2] = {nullptr, nullptr};  // [B + 1]: per-filter counts, or CSR offsets of the marker list
     int32_t* d_assoc = nullptr;
     cudaEvent_t ev_copied[2] = {nullptr, nullptr};
     cudaEvent_t ev_consumed[2] = {nullptr, nullptr};
@@ -926,7 +926,7 @@ int ekf_batch_create(int64_t B, int n, int device, ekf_batch** out) {
     for (int s = 0; s < 2; ++s) {
         CUB(cudaMalloc(&b->d_twists[s], sizeof(double) * 2 * (size_t)B));
         CUB(cudaMalloc(&b->d_vis[s], (size_t)n * B));
-        CUB(cudaMalloc(&b->d_count[s], sizeof(int32_t) * (size_t)B));
+        CUB(cudaMalloc(&b->d_count[s], sizeof(int32_t) * ((size_t)B + 1)));
         CUB(cudaEventCreateWithFlags(&b->ev_copied[s], cudaEventDisableTiming));
         CUB(cudaEventCreateWithFlags(&b->ev_consumed[s], cudaEventDisableTiming));
     }
@@ -990,6 +990,41 @@ int ekf_batch_step_known(ekf_batch* b, const double* twists, const double* xy, c
     CU(cudaEventRecord(b->ev_copied[s], b->copy_stream));
     CU(cudaStreamWaitEvent(b->stream, b->ev_copied[s], 0));
     int rc = ekf_batch_step_known_dev(b, b->d_twists[s], b->d_xy[s], b->d_vis[s]);
+    if (rc) return rc;
+    CU(cudaEventRecord(b->ev_consumed[s], b->stream));
+    return EKF_OK;
+}
+
+int ekf_batch_step_known_sparse_dev(ekf_batch* b, const double* d_twists, const int32_t* d_offsets, const uint8_t* d_ids,
+                                    const double* d_xy) {
+    if (!b || !d_twists || !d_offsets || !d_ids || !d_xy) return fail(EKF_ERR_INVALID, "null argument");
+    DeviceGuard g(b->device);
+    FusedParams p = batch_params(b, kDoPredict | kDoMeasurement | kSparseReadings, 1, d_twists, d_xy, d_ids, d_offsets,
+                                 nullptr);
+    int rc = launch_fused_sym(p, b->stream, b->device);
+    b->launches += 1;
+    return rc;
+}
+
+int ekf_batch_step_known_sparse(ekf_batch* b, const double* twists, const int32_t* offsets, const uint8_t* ids,
+                                const double* xy, int64_t total) {
+    if (!b || !twists || !offsets || total < 0 || (total > 0 && (!ids || !xy)))
+        return fail(EKF_ERR_INVALID, "null argument");
+    if (total > (int64_t)b->n * b->B) return fail(EKF_ERR_INVALID, "marker list longer than n markers per filter");
+    DeviceGuard g(b->device);
+    const int s = b->slot;
+    b->slot ^= 1;
+    const size_t B = (size_t)b->B;
+    CU(cudaStreamWaitEvent(b->copy_stream, b->ev_consumed[s], 0));
+    CU(cudaMemcpyAsync(b->d_twists[s], twists, sizeof(double) * 2 * B, cudaMemcpyHostToDevice, b->copy_stream));
+    CU(cudaMemcpyAsync(b->d_count[s], offsets, sizeof(int32_t) * (B + 1), cudaMemcpyHostToDevice, b->copy_stream));
+    if (total > 0) {
+        CU(cudaMemcpyAsync(b->d_vis[s], ids, (size_t)total, cudaMemcpyHostToDevice, b->copy_stream));
+        CU(cudaMemcpyAsync(b->d_xy[s], xy, sizeof(double) * 2 * (size_t)total, cudaMemcpyHostToDevice, b->copy_stream));
+    }
+    CU(cudaEventRecord(b->ev_copied[s], b->copy_stream));
+    CU(cudaStreamWaitEvent(b->stream, b->ev_copied[s], 0));
+    int rc = ekf_batch_step_known_sparse_dev(b, b->d_twists[s], b->d_count[s], b->d_vis[s], b->d_xy[s]);
     if (rc) return rc;
     CU(cudaEventRecord(b->ev_consumed[s], b->stream));
     return EKF_OK;

@@ -17,7 +17,7 @@
 
 namespace ekf {
 
-enum FusedMode : int { kDoPredict = 1, kDoMeasurement = 2, kDoAssociation = 4 };
+enum FusedMode : int { kDoPredict = 1, kDoMeasurement = 2, kDoAssociation = 4, kSparseReadings = 8 };
 
 struct FusedParams {
     double* sigma;         // [B][sig_stride]   row-major N x N per filter, stride padded to 16 doubles

@@ -106,6 +106,7 @@ __device__ __forceinline__ void sym_warp_gain(const double* __restrict__ sig, do
         ka[0] = Kpend[0], ka[1] = Kpend[1], ka[2] = Kpend[2], ka[3] = Kpend[i3], ka[4] = Kpend[i4];
         wa3 = Wpend[i3], wa4 = Wpend[i4];
     }
+    double2 wreg[NS];  // this lane's W columns stay in registers for the K loop
 #pragma unroll
     for (int sl = 0; sl < NS; ++sl) {
         const int c = lane + 32 * sl;
@@ -123,7 +124,8 @@ __device__ __forceinline__ void sym_warp_gain(const double* __restrict__ sig, do
                 s3 = apply_pair(s3, t3 ? kc : ka[3], t3 ? wa3 : wc);
                 s4 = apply_pair(s4, t4 ? kc : ka[4], t4 ? wa4 : wc);
             }
-            Wout[c] = make_double2(h_row0(h, s1, s2, s3, s4), h_row1(h, s0, s1, s2, s3, s4));
+            wreg[sl] = make_double2(h_row0(h, s1, s2, s3, s4), h_row1(h, s0, s1, s2, s3, s4));
+            Wout[c] = wreg[sl];
         }
     }
     __syncwarp();
@@ -139,7 +141,7 @@ __device__ __forceinline__ void sym_warp_gain(const double* __restrict__ sig, do
     for (int sl = 0; sl < NS; ++sl) {
         const int r = lane + 32 * sl;
         if (r < N) {
-            const double2 p = Wout[r];
+            const double2 p = wreg[sl];
             const double k0 = fma(p.y, si.i10, p.x * si.i00);
             const double k1 = fma(p.y, si.i11, p.x * si.i01);
             Kout[r] = make_double2(k0, k1);
@@ -324,9 +326,34 @@ __global__ void __launch_bounds__(32, NL == 20 ? EKF_SYM_MINB : 1) ekf_fused_sym
     }
     int init_flag = p.init_flag[b];
     int m = 0;
-    unsigned vis_reg = 0;  // visible flags of slots lane, lane + 32, ... (one bit each), fetched with the readings
-    if (p.mode & kDoMeasurement) {
-        for (int i = lane, k = 0; i < n; i += 32, ++k) vis_reg |= (p.vis[b * n + i] != 0 ? 1u : 0u) << k;
+    // visible landmarks as warp-uniform bit masks (slots 0..31 and 32..63), readings as {zr, ux, uy} per slot
+    unsigned vismask[2] = {0u, 0u};
+    int sp_begin = 0, sp_count = 0;
+    if ((p.mode & kDoMeasurement) && (p.mode & kSparseReadings)) {
+        // marker list: p.mcount = CSR offsets [B + 1], p.vis = landmark ids, p.xy = (x, y) per listed marker
+        sp_begin = p.mcount[b];
+        sp_count = p.mcount[b + 1] - sp_begin;
+        for (int k0 = 0; k0 < sp_count; k0 += 32) {
+            const int k = k0 + lane;
+            const bool on = k < sp_count;
+            int id = 0;
+            if (on) {
+                id = p.vis[sp_begin + k];
+                const Reading z = make_reading(p.xy[2 * (long long)(sp_begin + k)], p.xy[2 * (long long)(sp_begin + k) + 1]);
+                if (id < n) {
+                    zbuf[3 * id] = z.zr;
+                    zbuf[3 * id + 1] = z.ux;
+                    zbuf[3 * id + 2] = z.uy;
+                }
+            }
+            vismask[0] |= __reduce_or_sync(0xffffffffu, (on && id < 32 && id < n) ? 1u << id : 0u);
+            vismask[1] |= __reduce_or_sync(0xffffffffu, (on && id >= 32 && id < n) ? 1u << (id - 32) : 0u);
+        }
+    } else if (p.mode & kDoMeasurement) {
+        for (int base = 0; base < n; base += 32) {
+            const int i = base + lane;
+            vismask[base >> 5] = __ballot_sync(0xffffffffu, i < n && p.vis[b * n + i] != 0);
+        }
         // range and unit direction of every slot's reading, lane-parallel (ekf_slam.cpp:140-146)
         for (int i = lane; i < n; i += 32) {
             const Reading z = make_reading(p.xy[b * 2 * n + 2 * i], p.xy[b * 2 * n + 2 * i + 1]);
@@ -386,18 +413,37 @@ __global__ void __launch_bounds__(32, NL == 20 ? EKF_SYM_MINB : 1) ekf_fused_sym
     if (p.mode & kDoMeasurement) {
         const double theta = st[0], x = st[1], y = st[2];  // read once; stale for later i (:109-111)
         if (!init_flag) {
-            for (int i = lane; i < n; i += 32) {
-                double mx, my;
-                landmark_from_reading(p.xy[b * 2 * n + 2 * i], p.xy[b * 2 * n + 2 * i + 1], theta, x, y, mx, my);
-                st[3 + 2 * i] = mx;
-                st[4 + 2 * i] = my;
+            if (p.mode & kSparseReadings) {
+                // unlisted slots read (0, 0): the landmark starts at the robot's position, as with dense zeros
+                for (int i = lane; i < n; i += 32) {
+                    st[3 + 2 * i] = x;
+                    st[4 + 2 * i] = y;
+                }
+                __syncwarp();
+                for (int k = lane; k < sp_count; k += 32) {
+                    const int id = p.vis[sp_begin + k];
+                    if (id < n) {
+                        double mx, my;
+                        landmark_from_reading(p.xy[2 * (long long)(sp_begin + k)], p.xy[2 * (long long)(sp_begin + k) + 1],
+                                              theta, x, y, mx, my);
+                        st[3 + 2 * id] = mx;
+                        st[4 + 2 * id] = my;
+                    }
+                }
+            } else {
+                for (int i = lane; i < n; i += 32) {
+                    double mx, my;
+                    landmark_from_reading(p.xy[b * 2 * n + 2 * i], p.xy[b * 2 * n + 2 * i + 1], theta, x, y, mx, my);
+                    st[3 + 2 * i] = mx;
+                    st[4 + 2 * i] = my;
+                }
             }
             init_flag = 1;
             __syncwarp();
         }
         if (!have_sincos) sincos(theta, &sth, &cth);
         for (int base = 0; base < n; base += 32) {
-            unsigned rem = __ballot_sync(0xffffffffu, (vis_reg >> (base >> 5)) & 1u);
+            unsigned rem = vismask[base >> 5];
             // Visible landmarks go through in PAIRS: both gains first (the second sees the first one's factor as
             // pending), then ONE pass over Sigma applies both rank-2 updates.  H_j / nu of the next landmark are
             // evaluated right after the state update they depend on and before the pass, so the scalar chain

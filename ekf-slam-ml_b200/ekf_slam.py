@@ -253,6 +253,20 @@ def _ptr(a):
     return int(a)
 
 
+def marker_list(xy, visible):
+    """Dense fake-sensor arrays ([B,2n] readings, [B,n] visible flags) -> the marker list step_known_sparse() takes:
+    (offsets [B+1] int32, ids [total] uint8, xy [total,2]); only visible markers are listed, in id order."""
+    vis = np.asarray(visible) != 0
+    B, n = vis.shape
+    if n > 255:
+        raise ValueError("marker ids are uint8")
+    offsets = np.zeros(B + 1, dtype=np.int32)
+    np.cumsum(vis.sum(axis=1), out=offsets[1:])
+    rows, ids = np.nonzero(vis)
+    pts = np.asarray(xy, dtype=np.float64).reshape(B, n, 2)[rows, ids]
+    return offsets, ids.astype(np.uint8), np.ascontiguousarray(pts)
+
+
 class EKFBatch:
     """B independent reference-sized filters on one GPU (Monte-Carlo noise-seed sweep)."""
 
@@ -275,6 +289,12 @@ class EKFBatch:
     def step_known(self, twists, xy, visible):
         """prediction + measurement for every filter; host arrays [B,2], [B,2n], [B,n] (uint8)."""
         check(self._L.ekf_batch_step_known(self._h, _ptr(twists), _ptr(xy), _ptr(visible)))
+
+    def step_known_sparse(self, twists, offsets, ids, xy, total=None):
+        """prediction + measurement from the marker list (visible markers only): twists [B,2], CSR offsets [B+1] int32,
+        ids [total] uint8, xy [total,2].  Bit-identical to step_known() on the dense arrays (unlisted slots = 0)."""
+        total = int(offsets[-1]) if total is None else int(total)
+        check(self._L.ekf_batch_step_known_sparse(self._h, _ptr(twists), _ptr(offsets), _ptr(ids), _ptr(xy), total))
 
     def step_unknown(self, twists, meas, count, m_max, want_assoc=False):
         """prediction + data_association; host arrays [B,2], [B,m_max,2], [B] int32."""

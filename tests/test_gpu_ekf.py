@@ -188,6 +188,35 @@ def test_batch_matches_per_filter_oracle(gpu_pkg):
     assert err[3] == B and np.all(err[:3] / B < 0.05 ** 2)
 
 
+@pytest.mark.parametrize("n", [20, 40])
+def test_batch_marker_list_equals_dense_arrays(gpu_pkg, n):
+    """The fake_sensor marker list (visible markers only, CSR) gives bit-identical filters to the dense arrays the
+    SLAM node unpacks it into (nuslam/src/slam.cpp:232-262), including the first call that initialises every slot."""
+    tg = gpu_pkg.tracegen
+    B, T = 200, 10
+    tr = tg.simulate_known(tg.grid_world(8, 5, pitch=0.35) if n != 20 else tg.dense_world(20), B, T, seed=11)
+    dense, sparse = gpu_pkg.EKFBatch(B, n), gpu_pkg.EKFBatch(B, n)
+    for t in range(T):
+        tw = np.ascontiguousarray(tr["twists"][t])
+        xy = np.ascontiguousarray(tr["xy"][t]) * tr["vis"][t].repeat(2, axis=1)  # unlisted slots read (0, 0)
+        vis = np.ascontiguousarray(tr["vis"][t])
+        dense.step_known(tw, xy, vis)
+        off, ids, pts = gpu_pkg.marker_list(xy, vis)
+        assert off[-1] == vis.sum() and len(ids) == off[-1]
+        sparse.step_known_sparse(tw, off, ids, pts)
+        dense.sync()
+        sparse.sync()
+    assert sparse.update_count == dense.update_count == int(tr["vis"].sum())
+    assert np.array_equal(sparse.states(), dense.states())
+    for b in (0, B // 2, B - 1):
+        assert np.array_equal(sparse.sigma(b), dense.sigma(b))
+    # an empty list is a prediction-only step
+    before = sparse.states()
+    sparse.step_known_sparse(np.zeros((B, 2)), np.zeros(B + 1, np.int32), np.zeros(0, np.uint8), np.zeros((0, 2)))
+    sparse.sync()
+    assert np.array_equal(sparse.states(), before)
+
+
 def test_batch_unknown_matches_oracle(gpu_pkg):
     tg = gpu_pkg.tracegen
     B, T, M = 40, 30, 10
