@@ -3,8 +3,7 @@
 // The reference applies Sigma <- Sigma - K W after every landmark correction (ekf_slam.cpp:191-192); for a large
 // map that is one full HBM read + write of Sigma per correction.  Here up to kMaxPending corrections are kept as
 // factor pairs (K_j, W_j) and applied in ONE sweep:  Sigma <- Sigma - sum_j K_j W_j.  The next correction only needs
-// five rows and five columns of the CURRENT covariance; they are rebuilt on the fly from Sigma_0 and the pending
-// factors.  Every element goes through exactly the same sequence of FMAs as with sequential sweeps
+// five rows of the CURRENT covariance; they are rebuilt on the fly from Sigma_0 and the pending factors.  Every element goes through exactly the same sequence of FMAs as with sequential sweeps
 // (v = fma(-k.y, w.y, fma(-k.x, w.x, v)) for j = 0, 1, ...), so the result is bit-identical — only the HBM traffic
 // changes: 16 N^2 bytes per SWEEP instead of per correction.
 #pragma once
@@ -20,8 +19,7 @@ struct GainSharedP {
     double nu0, nu1;
     int i3;
     int active;
-    double2 Kidx[kMaxPending][5];  // K_j[idx_l]
-    double2 Widx[kMaxPending][5];  // W_j[idx_l]
+    double2 Kidx[kMaxPending][5];  // K_j[idx_a], a = 0..4
 };
 
 __device__ __forceinline__ double apply_factor(double v, double2 k, double2 w) {
@@ -30,12 +28,19 @@ __device__ __forceinline__ double apply_factor(double v, double2 k, double2 w) {
 
 // Correction number `p` of the current group: writes (K_p, W_p), reads Sigma_0 and the factors j < p.
 // state_in is never written (the new state goes to state_out), so no CTA can observe a half-updated state.
+//
+// W = Hj Sigma comes from the five ROWS {0, 1, 2, 3+2i, 4+2i} of the current covariance (coalesced), rebuilt from
+// Sigma_0 and the pending factors; K = Sigma Hj^T S^-1 is formed as W^T S^-1 (ekf_slam.cpp:178 with Sigma = Sigma^T,
+// which the reference's (I - K H) Sigma keeps to rounding) so no strided column of Sigma is touched.
+// The O(1) part (S from the 5 x 5 block, its inverse, the innovation) is done by the first warp of every CTA with one
+// block entry per lane, so that its global loads are one round trip instead of a serial chain.
 __global__ void __launch_bounds__(256)
     k_large_gain_p(const double* __restrict__ sig, long long ld, int N, const double* __restrict__ state_in,
                    double* __restrict__ state_out, const double* __restrict__ pose_src, const UpdateCmd* __restrict__ cmd,
                    int lm_arg, double sx_arg, double sy_arg, double2* __restrict__ Kp, double2* __restrict__ Wp, int p) {
     __shared__ GainSharedP g;
-    if (threadIdx.x == 0) {
+    if (threadIdx.x < 32) {
+        const int lane = threadIdx.x;
         int lm = lm_arg;
         double sx = sx_arg, sy = sy_arg;
         int active = 1;
@@ -45,39 +50,44 @@ __global__ void __launch_bounds__(256)
             sx = cmd->sx;
             sy = cmd->sy;
         }
-        g.active = active;
+        if (lane == 0) g.active = active;
         if (active) {
             const int i3 = 3 + 2 * lm;
+            const int a = lane < 25 ? lane / 5 : 0, l = lane < 25 ? lane - 5 * (lane / 5) : 0;
+            const long long ida = a < 3 ? a : i3 + (a - 3), idl = l < 3 ? l : i3 + (l - 3);
             const double theta = pose_src[0], x = pose_src[1], y = pose_src[2];
             const Hj h = make_hj(state_in[i3], state_in[i3 + 1], theta, x, y);
-            const long long id[5] = {0, 1, 2, i3, i3 + 1};
-            for (int j = 0; j < p; ++j)
-                for (int l = 0; l < 5; ++l) {
-                    g.Kidx[j][l] = Kp[(long long)j * ld + id[l]];
-                    g.Widx[j][l] = Wp[(long long)j * ld + id[l]];
-                }
-            double w0[5], w1[5];
-            for (int l = 0; l < 5; ++l) {
-                double s[5];
-                for (int a = 0; a < 5; ++a) {
-                    double v = sig[id[a] * ld + id[l]];
-                    for (int j = 0; j < p; ++j) v = apply_factor(v, g.Kidx[j][a], g.Widx[j][l]);
-                    s[a] = v;
-                }
-                w0[l] = h_row0(h, s[1], s[2], s[3], s[4]);
-                w1[l] = h_row1(h, s[0], s[1], s[2], s[3], s[4]);
+            double v = sig[ida * ld + idl];  // Sigma(id_a, id_l), then the pending factors in order
+            for (int j = 0; j < p; ++j) {
+                const double2 kja = Kp[(long long)j * ld + ida];
+                const double2 wjl = Wp[(long long)j * ld + idl];
+                v = apply_factor(v, kja, wjl);
+                if (l == 0 && lane < 25) g.Kidx[j][a] = kja;
             }
-            const double s00 = h_row0(h, w0[1], w0[2], w0[3], w0[4]) + kR;
-            const double s01 = h_row1(h, w0[0], w0[1], w0[2], w0[3], w0[4]);
-            const double s10 = h_row0(h, w1[1], w1[2], w1[3], w1[4]);
-            const double s11 = h_row1(h, w1[0], w1[1], w1[2], w1[3], w1[4]) + kR;
-            g.h = h;
-            g.si = inv2x2(s00, s01, s10, s11);
-            double zr, zphi;
-            range_bearing(sx, sy, zr, zphi);
-            g.nu0 = __dsub_rn(zr, h.zr);
-            g.nu1 = normalize_angle(__dsub_rn(zphi, h.zphi));
-            g.i3 = i3;
+            // column l of the block: s[a'] = Sigma(id_a', id_l) sits in lane 5 a' + l
+            const double s0 = __shfl_sync(0xffffffffu, v, l), s1 = __shfl_sync(0xffffffffu, v, 5 + l),
+                         s2 = __shfl_sync(0xffffffffu, v, 10 + l), s3 = __shfl_sync(0xffffffffu, v, 15 + l),
+                         s4 = __shfl_sync(0xffffffffu, v, 20 + l);
+            const double w0 = h_row0(h, s1, s2, s3, s4), w1 = h_row1(h, s0, s1, s2, s3, s4);  // W[:, id_l]
+            double a0[5], a1[5];
+#pragma unroll
+            for (int c = 0; c < 5; ++c) {  // lanes 0..4 hold columns 0..4
+                a0[c] = __shfl_sync(0xffffffffu, w0, c);
+                a1[c] = __shfl_sync(0xffffffffu, w1, c);
+            }
+            if (lane == 0) {
+                const double s00 = h_row0(h, a0[1], a0[2], a0[3], a0[4]) + kR;
+                const double s01 = h_row1(h, a0[0], a0[1], a0[2], a0[3], a0[4]);
+                const double s10 = h_row0(h, a1[1], a1[2], a1[3], a1[4]);
+                const double s11 = h_row1(h, a1[0], a1[1], a1[2], a1[3], a1[4]) + kR;
+                g.h = h;
+                g.si = inv2x2(s00, s01, s10, s11);
+                double zr, zphi;
+                range_bearing(sx, sy, zr, zphi);
+                g.nu0 = __dsub_rn(zr, h.zr);
+                g.nu1 = normalize_angle(__dsub_rn(zphi, h.zphi));
+                g.i3 = i3;
+            }
         }
     }
     __syncthreads();
@@ -94,28 +104,21 @@ __global__ void __launch_bounds__(256)
     const Hj h = g.h;
     const int i3 = g.i3, i4 = i3 + 1;
     double s0 = sig[k], s1 = sig[ld + k], s2 = sig[2 * ld + k], s3 = sig[i3 * ld + k], s4 = sig[i4 * ld + k];
-    const double* row = sig + k * ld;
-    double r0 = row[0], r1 = row[1], r2 = row[2], r3 = row[i3], r4 = row[i4];
+    const double st_k = state_in[k];
     for (int j = 0; j < p; ++j) {
         const double2 wj = Wp[(long long)j * ld + k];  // W_j[:, k]
-        const double2 kj = Kp[(long long)j * ld + k];  // K_j[k, :]
         s0 = apply_factor(s0, g.Kidx[j][0], wj);
         s1 = apply_factor(s1, g.Kidx[j][1], wj);
         s2 = apply_factor(s2, g.Kidx[j][2], wj);
         s3 = apply_factor(s3, g.Kidx[j][3], wj);
         s4 = apply_factor(s4, g.Kidx[j][4], wj);
-        r0 = apply_factor(r0, kj, g.Widx[j][0]);
-        r1 = apply_factor(r1, kj, g.Widx[j][1]);
-        r2 = apply_factor(r2, kj, g.Widx[j][2]);
-        r3 = apply_factor(r3, kj, g.Widx[j][3]);
-        r4 = apply_factor(r4, kj, g.Widx[j][4]);
     }
-    Wout[k] = make_double2(h_row0(h, s1, s2, s3, s4), h_row1(h, s0, s1, s2, s3, s4));
-    const double p0 = h_row0(h, r1, r2, r3, r4), p1 = h_row1(h, r0, r1, r2, r3, r4);
+    const double p0 = h_row0(h, s1, s2, s3, s4), p1 = h_row1(h, s0, s1, s2, s3, s4);
+    Wout[k] = make_double2(p0, p1);
     const double k0 = fma(p1, g.si.i10, p0 * g.si.i00);
     const double k1 = fma(p1, g.si.i11, p0 * g.si.i01);
     Kout[k] = make_double2(k0, k1);
-    double ns = state_in[k] + fma(k1, g.nu1, k0 * g.nu0);
+    double ns = st_k + fma(k1, g.nu1, k0 * g.nu0);
     if (k == 0) ns = normalize_angle(ns);  // ekf_slam.cpp:187
     state_out[k] = ns;
 }
