@@ -100,7 +100,14 @@ __device__ __forceinline__ void sym_warp_gain(const double* __restrict__ sig, do
     constexpr int NS = NL ? (3 + 2 * NL + 31) / 32 : 5;  // column slots per lane (n <= 64 -> N <= 131)
     const int i3 = 3 + 2 * i, i4 = i3 + 1;
     const int b3 = i3 & ~15, b4 = i4 & ~15;
-    const int row3 = stair_row_base(i3, N) - b3, row4 = stair_row_base(i4, N) - b4;
+    // row offsets of the landmark's two rows: lane r % 32 already holds stair_row_base(r) - (r & ~15) in cmv[r / 32]
+    int row3 = __shfl_sync(0xffffffffu, cmv[0], i3 & 31), row4 = __shfl_sync(0xffffffffu, cmv[0], i4 & 31);
+#pragma unroll
+    for (int sl = 1; sl < NS; ++sl) {
+        const int r3 = __shfl_sync(0xffffffffu, cmv[sl], i3 & 31), r4 = __shfl_sync(0xffffffffu, cmv[sl], i4 & 31);
+        if ((i3 >> 5) == sl) row3 = r3;
+        if ((i4 >> 5) == sl) row4 = r4;
+    }
     double2 ka[5], wa3, wa4;
     if (PEND) {
         ka[0] = Kpend[0], ka[1] = Kpend[1], ka[2] = Kpend[2], ka[3] = Kpend[i3], ka[4] = Kpend[i4];
@@ -280,6 +287,12 @@ __device__ __forceinline__ double sym_maha_distance(const double* __restrict__ s
     return __dadd_rn(__dmul_rn(t0, v0), __dmul_rn(t1, v1));
 }
 
+// first-call / new-landmark initialisation happens once per landmark: keep its atan2 + sincos out of the hot code
+static __device__ __noinline__ void landmark_from_reading_cold(double sx, double sy, double theta, double x, double y,
+                                                               double& mx, double& my) {
+    landmark_from_reading(sx, sy, theta, x, y, mx, my);
+}
+
 template <int NL>
 __global__ void __launch_bounds__(32, NL == 20 ? EKF_SYM_MINB : 1) ekf_fused_sym_kernel(const FusedParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -424,7 +437,7 @@ __global__ void __launch_bounds__(32, NL == 20 ? EKF_SYM_MINB : 1) ekf_fused_sym
                     const int id = p.vis[sp_begin + k];
                     if (id < n) {
                         double mx, my;
-                        landmark_from_reading(p.xy[2 * (long long)(sp_begin + k)], p.xy[2 * (long long)(sp_begin + k) + 1],
+                        landmark_from_reading_cold(p.xy[2 * (long long)(sp_begin + k)], p.xy[2 * (long long)(sp_begin + k) + 1],
                                               theta, x, y, mx, my);
                         st[3 + 2 * id] = mx;
                         st[4 + 2 * id] = my;
@@ -433,7 +446,7 @@ __global__ void __launch_bounds__(32, NL == 20 ? EKF_SYM_MINB : 1) ekf_fused_sym
             } else {
                 for (int i = lane; i < n; i += 32) {
                     double mx, my;
-                    landmark_from_reading(p.xy[b * 2 * n + 2 * i], p.xy[b * 2 * n + 2 * i + 1], theta, x, y, mx, my);
+                    landmark_from_reading_cold(p.xy[b * 2 * n + 2 * i], p.xy[b * 2 * n + 2 * i + 1], theta, x, y, mx, my);
                     st[3 + 2 * i] = mx;
                     st[4 + 2 * i] = my;
                 }
@@ -541,7 +554,7 @@ __global__ void __launch_bounds__(32, NL == 20 ? EKF_SYM_MINB : 1) ekf_fused_sym
             if (min_idx == known_count && min_idx < n) {  // :318-327
                 if (lane == 0) {
                     double mx, my;
-                    landmark_from_reading(p.xy[o * 2], p.xy[o * 2 + 1], theta, x, y, mx, my);
+                    landmark_from_reading_cold(p.xy[o * 2], p.xy[o * 2 + 1], theta, x, y, mx, my);
                     st[3 + 2 * min_idx] = mx;
                     st[4 + 2 * min_idx] = my;
                 }

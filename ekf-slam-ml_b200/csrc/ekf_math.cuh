@@ -36,7 +36,7 @@ constexpr double kSmallTurn = 0.000001;  // ekf_slam.cpp:79
 // fmod(x, 2*pi), exact like the C library's: the quotient is small on this path, so one FMA recovers the
 // remainder exactly (x and q*2pi are both multiples of ulp(2pi) once |x| >= 2pi, and the remainder is
 // below 8 so it fits 53 bits).  Falls back to fmod() for large or non-finite arguments.
-__device__ __forceinline__ double fmod_2pi(double x) {
+static __device__ __noinline__ double fmod_2pi(double x) {
     const double y = kTwoPi;
     const double ax = fabs(x);
     if (ax < y) return x;
@@ -58,15 +58,16 @@ __device__ __forceinline__ double fmod_2pi(double x) {
 // For |rad| < 2pi (every angle on this path: sums and differences of two wrapped angles) the first fmod is the
 // identity and the second one reduces t = rad + 2pi in [0, 4pi): t - 2pi is exact there (Sterbenz), so the result is
 // bit-identical to the library formulation without a division or a truncation.
+static __device__ __noinline__ double normalize_angle_large(double rad) {  // |rad| >= 2pi: never on the hot path
+    const double reduced = fmod_2pi(rad);
+    double ang = fmod_2pi(__dadd_rn(reduced, kTwoPi));
+    if (ang > kPi) ang = __dsub_rn(ang, kTwoPi);
+    return ang;
+}
 __device__ __forceinline__ double normalize_angle(double rad) {
-    double ang;
-    if (fabs(rad) < kTwoPi) {
-        const double t = __dadd_rn(rad, kTwoPi);
-        ang = (t >= kTwoPi) ? __dsub_rn(t, kTwoPi) : t;
-    } else {
-        const double reduced = fmod_2pi(rad);
-        ang = fmod_2pi(__dadd_rn(reduced, kTwoPi));
-    }
+    if (!(fabs(rad) < kTwoPi)) return normalize_angle_large(rad);
+    const double t = __dadd_rn(rad, kTwoPi);
+    double ang = (t >= kTwoPi) ? __dsub_rn(t, kTwoPi) : t;
     if (ang > kPi) ang = __dsub_rn(ang, kTwoPi);
     return ang;
 }
