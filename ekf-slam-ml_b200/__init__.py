@@ -7,8 +7,8 @@ from . import _lib, sharding, tracegen
 from ._lib import EkfError, device_count
 from .circle_fitting import CircleFitting
 from .tube_world import TubeWorld
-from .ekf_slam import (EKF_SLAM, ENGINE_AUTO, ENGINE_FUSED, ENGINE_STREAM, EKFBatch, PinnedBuffer, Twist2D,
-                       Vector2D, body_twist, marker_list, normalize_angle)
+from .ekf_slam import (DiffDrive, EKF_SLAM, ENGINE_AUTO, ENGINE_FUSED, ENGINE_STREAM, EKFBatch, PinnedBuffer, Twist2D,
+                       Vector2D, body_twist, marker_list, normalize_angle, update_pose)
 
-__all__ = ["EKF_SLAM", "EKFBatch", "PinnedBuffer", "Twist2D", "Vector2D", "body_twist", "marker_list", "normalize_angle",
+__all__ = ["DiffDrive", "update_pose", "EKF_SLAM", "EKFBatch", "PinnedBuffer", "Twist2D", "Vector2D", "body_twist", "marker_list", "normalize_angle",
            "EkfError", "device_count", "tracegen", "sharding", "CircleFitting", "TubeWorld", "ENGINE_AUTO", "ENGINE_FUSED", "ENGINE_STREAM"]

@@ -84,6 +84,8 @@ SIGNATURES = {
     "ekf_batch_timer_stop": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_float)]),
     "ekf_batch_launch_count": (ctypes.c_int, [ctypes.c_void_p, c_u64_p]),
     "ekf_normalize_angles": (ctypes.c_int, [c_double_p, c_double_p, ctypes.c_int64, ctypes.c_int]),
+    "ekf_update_pose": (ctypes.c_int, [ctypes.c_double, ctypes.c_double, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p,
+                                       ctypes.c_void_p]),
     "ekf_body_twist": (ctypes.c_int, [ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_double, c_double_p]),
     # include/circle_fit_b200.h
     "circles_last_error": (ctypes.c_char_p, []),
@@ -111,6 +113,7 @@ SIGNATURES = {
     "tubeworld_step_scan": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int]),
     "tubeworld_outputs": (ctypes.c_int, [ctypes.c_void_p, c_void_pp, c_void_pp, c_void_pp, c_void_pp, c_void_pp]),
     "tubeworld_download": (ctypes.c_int, [ctypes.c_void_p, c_double_p, c_double_p, c_u8_p, c_double_p, c_float_p]),
+    "tubeworld_odometry": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     "tubeworld_sync": (ctypes.c_int, [ctypes.c_void_p]),
     "tubeworld_stream": (ctypes.c_void_p, [ctypes.c_void_p]),
     "tubeworld_set_stream": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),

@@ -139,6 +139,15 @@ __global__ void k_maha_one(const double* sig, long long ld, const double* state,
     *out = maha_distance(sig, ld, i, state[3 + 2 * i], state[4 + 2 * i], zr, zphi, state[0], state[1], state[2]);
 }
 
+__global__ void k_update_pose(double wheel_base, double wheel_radius, long long count, double* poses,
+                              const double* left, const double* right) {
+    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= count) return;
+    double x = poses[3 * k], y = poses[3 * k + 1], th = poses[3 * k + 2];
+    update_pose(wheel_base, wheel_radius, left[k], right[k], x, y, th);
+    poses[3 * k] = x, poses[3 * k + 1] = y, poses[3 * k + 2] = th;
+}
+
 __global__ void k_normalize(const double* in, double* out, long long count) {
     const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (k < count) out[k] = normalize_angle(in[k]);
@@ -1205,6 +1214,37 @@ int ekf_normalize_angles(const double* in, double* out, int64_t count, int devic
     CU(cudaMemcpy(out, d_out, sizeof(double) * count, cudaMemcpyDeviceToHost));
     cudaFree(d_in);
     cudaFree(d_out);
+    return EKF_OK;
+}
+
+// DiffDrive::updatePose for `count` independent odometers (rigid2d/src/diff_drive.cpp:50-67, integrateTwist
+// rigid2d.cpp:304-333): poses [count][3] = {x, y, theta} in place, left / right wheel angle increments [count].
+int ekf_update_pose(double wheel_base, double wheel_radius, int64_t count, double* poses, const double* left,
+                    const double* right) {
+    if (count < 0 || (count > 0 && (!poses || !left || !right))) return fail(EKF_ERR_INVALID, "invalid argument");
+    if (count == 0) return EKF_OK;
+    int ndev = 0;
+    int rc = ekf_device_count(&ndev);
+    if (rc) return rc;
+    double *d_p = nullptr, *d_l = nullptr, *d_r = nullptr;
+    cudaError_t e = cudaMalloc(&d_p, sizeof(double) * 3 * (size_t)count);
+    if (e == cudaSuccess) e = cudaMalloc(&d_l, sizeof(double) * (size_t)count);
+    if (e == cudaSuccess) e = cudaMalloc(&d_r, sizeof(double) * (size_t)count);
+    if (e == cudaSuccess) e = cudaMemcpy(d_p, poses, sizeof(double) * 3 * (size_t)count, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(d_l, left, sizeof(double) * (size_t)count, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(d_r, right, sizeof(double) * (size_t)count, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        k_update_pose<<<(unsigned)((count + 255) / 256), 256>>>(wheel_base, wheel_radius, count, d_p, d_l, d_r);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpy(poses, d_p, sizeof(double) * 3 * (size_t)count, cudaMemcpyDeviceToHost);
+    cudaFree(d_p);
+    cudaFree(d_l);
+    cudaFree(d_r);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail((int)e, "ekf_update_pose: %s", cudaGetErrorString(e));
+    }
     return EKF_OK;
 }
 

@@ -298,6 +298,46 @@ __device__ __forceinline__ Motion motion_model(double theta, double dtheta, doub
     return m;
 }
 
+// ---- dead-reckoning odometry (DiffDrive::updatePose, rigid2d/src/diff_drive.cpp:50-67) --------------------------
+// Transform2D::operator*=, rigid2d.cpp:222-245: the composed rotation goes through acos / asin, kept as written.
+__device__ __forceinline__ void compose_tf(double ax, double ay, double ath, double bx, double by, double bth,
+                                           double& ox, double& oy, double& oth) {
+    double sa, ca, sb, cb;
+    sincos(ath, &sa, &ca);
+    sincos(bth, &sb, &cb);
+    const double r11 = __dsub_rn(__dmul_rn(ca, cb), __dmul_rn(sa, sb));
+    const double r21 = __dadd_rn(__dmul_rn(sa, cb), __dmul_rn(ca, sb));
+    const double rc = acos(r11), rs = asin(r21);
+    oth = (__dmul_rn(rc, rs) < 0) ? rs : rc;
+    ox = __dadd_rn(__dsub_rn(__dmul_rn(bx, ca), __dmul_rn(by, sa)), ax);
+    oy = __dadd_rn(__dadd_rn(__dmul_rn(bx, sa), __dmul_rn(by, ca)), ay);
+}
+// integrateTwist, rigid2d.cpp:304-333
+__device__ __forceinline__ void integrate_twist(double w, double vx, double vy, double& tx, double& ty, double& tth) {
+    if (fabs(w) > 0.0001) {
+        const double xs = vy / w, ys = -vx / w;
+        double t1x, t1y, t1th;
+        compose_tf(0.0, 0.0, w, xs, ys, 0.0, t1x, t1y, t1th);  // Transform2D(w) * Transform2D(p_sb)
+        compose_tf(-xs, -ys, -0.0, t1x, t1y, t1th, tx, ty, tth);  // t_sb.inv() * (...)
+    } else {
+        tx = vx, ty = vy, tth = 0.0;
+    }
+}
+// pose = {x, y, theta} in place; theta is not wrapped
+__device__ __forceinline__ void update_pose(double wheel_base, double wheel_radius, double left, double right, double& x,
+                                            double& y, double& theta) {
+    const double D = __dmul_rn(wheel_base, 0.5), r = wheel_radius;
+    const double w = __dmul_rn(r / __dmul_rn(2.0, D), __dsub_rn(right, left));
+    const double vx = __dmul_rn(r / 2.0, __dadd_rn(right, left));
+    double tx, ty, tth;
+    integrate_twist(w, vx, 0.0, tx, ty, tth);
+    double s, c;
+    sincos(theta, &s, &c);
+    x = __dadd_rn(x, __dsub_rn(__dmul_rn(tx, c), __dmul_rn(ty, s)));
+    y = __dadd_rn(y, __dadd_rn(__dmul_rn(tx, s), __dmul_rn(ty, c)));
+    theta = __dadd_rn(theta, tth);
+}
+
 // Lexicographic (distance, index) minimum used by the association argmin: strict '<' on distance,
 // lowest index on ties (ekf_slam.cpp:300-309).  NaNs must be mapped to +inf by the caller.
 __device__ __forceinline__ bool better(double d_a, int i_a, double d_b, int i_b) {

@@ -45,13 +45,15 @@ __device__ __forceinline__ unsigned long long ctr_of(long long tick, int purpose
 
 struct Robots {
     double *x, *y, *th, *v, *om, *dl, *dr;
+    double *ox, *oy, *oth;  // dead-reckoning odometer (slam.cpp:96): same wheel increments, no collisions
 };
 
 // one simulator tick of one robot (tube_world.cpp:193-250, 316-366), tracegen.TubeWorldSim.step_tick
 __device__ __forceinline__ void tick_once(const tubeworld_params& p, const double* __restrict__ tx,
                                           const double* __restrict__ ty, int n_tubes, unsigned long long seed,
                                           unsigned long long fid, long long tick, double& x, double& y, double& th,
-                                          double& v, double& om, double& dl, double& dr) {
+                                          double& v, double& om, double& dl, double& dr, double& ox, double& oy,
+                                          double& oth) {
     if (tick % 10 == 0) {
         v = p.cmd_v + p.vx_std * hash_normal(seed, fid, ctr_of(tick, 0, 0));
         om = p.cmd_v / p.cmd_radius + p.the_std * hash_normal(seed, fid, ctr_of(tick, 1, 0));
@@ -78,6 +80,11 @@ __device__ __forceinline__ void tick_once(const tubeworld_params& p, const doubl
     x = x + c * bx - s * by;
     y = y + s * bx + c * by;
     th = th + dth;
+    double so_, co_;
+    sincos(oth, &so_, &co_);
+    ox = ox + co_ * bx - so_ * by;
+    oy = oy + so_ * bx + co_ * by;
+    oth = oth + dth;
     const double lim = p.tube_radius + p.wheel_base / 2;
     for (int j = 0; j < n_tubes; ++j) {  // first tube closer than the limit snaps the robot back
         const double dx = tx[j] - x, dy = ty[j] - y;
@@ -96,13 +103,17 @@ __global__ void __launch_bounds__(128)
     k_step_known(tubeworld_params p, const double* __restrict__ tx, const double* __restrict__ ty, int n_tubes,
                  unsigned long long seed, long long first_filter, long long B, long long tick0, int n_ticks, Robots R,
                  int report_visible, double* __restrict__ twists, double* __restrict__ xy, uint8_t* __restrict__ vis,
-                 double* __restrict__ truth) {
+                 double* __restrict__ truth, double* __restrict__ odom) {
     const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
     const unsigned long long fid = (unsigned long long)(first_filter + b);
     double x = R.x[b], y = R.y[b], th = R.th[b], v = R.v[b], om = R.om[b], dl = R.dl[b], dr = R.dr[b];
-    for (int k = 0; k < n_ticks; ++k) tick_once(p, tx, ty, n_tubes, seed, fid, tick0 + k, x, y, th, v, om, dl, dr);
+    double ox = R.ox[b], oy = R.oy[b], oth = R.oth[b];
+    for (int k = 0; k < n_ticks; ++k)
+        tick_once(p, tx, ty, n_tubes, seed, fid, tick0 + k, x, y, th, v, om, dl, dr, ox, oy, oth);
     R.x[b] = x, R.y[b] = y, R.th[b] = th, R.v[b] = v, R.om[b] = om, R.dl[b] = dl, R.dr[b] = dr;
+    R.ox[b] = ox, R.oy[b] = oy, R.oth[b] = oth;
+    odom[3 * b] = ox, odom[3 * b + 1] = oy, odom[3 * b + 2] = oth;
     const long long tick = tick0 + n_ticks;
     // odometry twist handed to prediction(): getBodyTwistForUpdate(10 dl, 10 dr)  (slam.cpp:173-176)
     const double D = p.wheel_base * 0.5, r = p.wheel_radius;
@@ -133,13 +144,17 @@ __global__ void __launch_bounds__(128)
 __global__ void __launch_bounds__(128)
     k_advance(tubeworld_params p, const double* __restrict__ tx, const double* __restrict__ ty, int n_tubes,
               unsigned long long seed, long long first_filter, long long B, long long tick0, int n_ticks, Robots R,
-              double* __restrict__ twists, double* __restrict__ truth) {
+              double* __restrict__ twists, double* __restrict__ truth, double* __restrict__ odom) {
     const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
     const unsigned long long fid = (unsigned long long)(first_filter + b);
     double x = R.x[b], y = R.y[b], th = R.th[b], v = R.v[b], om = R.om[b], dl = R.dl[b], dr = R.dr[b];
-    for (int k = 0; k < n_ticks; ++k) tick_once(p, tx, ty, n_tubes, seed, fid, tick0 + k, x, y, th, v, om, dl, dr);
+    double ox = R.ox[b], oy = R.oy[b], oth = R.oth[b];
+    for (int k = 0; k < n_ticks; ++k)
+        tick_once(p, tx, ty, n_tubes, seed, fid, tick0 + k, x, y, th, v, om, dl, dr, ox, oy, oth);
     R.x[b] = x, R.y[b] = y, R.th[b] = th, R.v[b] = v, R.om[b] = om, R.dl[b] = dl, R.dr[b] = dr;
+    R.ox[b] = ox, R.oy[b] = oy, R.oth[b] = oth;
+    odom[3 * b] = ox, odom[3 * b + 1] = oy, odom[3 * b + 2] = oth;
     const double D = p.wheel_base * 0.5, r = p.wheel_radius;
     const double l10 = dl * 10.0, r10 = dr * 10.0;
     twists[2 * b] = (r / (2.0 * D)) * (r10 - l10);
@@ -238,9 +253,9 @@ struct tubeworld {
     tubeworld_params p{};
     cudaStream_t stream = nullptr;
     double *d_tx = nullptr, *d_ty = nullptr;
-    double* d_robots = nullptr;  // 7 arrays of B
+    double* d_robots = nullptr;  // 10 arrays of B
     tw::Robots R{};
-    double *d_twists = nullptr, *d_xy = nullptr, *d_truth = nullptr;
+    double *d_twists = nullptr, *d_xy = nullptr, *d_truth = nullptr, *d_odom = nullptr;
     uint8_t* d_vis = nullptr;
     float* d_ranges = nullptr;
 };
@@ -261,6 +276,7 @@ int tubeworld_destroy(tubeworld* w) {
     cudaFree(w->d_twists);
     cudaFree(w->d_xy);
     cudaFree(w->d_truth);
+    cudaFree(w->d_odom);
     cudaFree(w->d_vis);
     cudaFree(w->d_ranges);
     if (w->stream && w->own_stream) cudaStreamDestroy(w->stream);
@@ -298,14 +314,15 @@ int tubeworld_create(int64_t B, const tubeworld_params* p, const double* tubes_x
     };
     A((void**)&w->d_tx, sizeof(double) * n_tubes);
     A((void**)&w->d_ty, sizeof(double) * n_tubes);
-    A((void**)&w->d_robots, sizeof(double) * 7 * (size_t)B);
+    A((void**)&w->d_robots, sizeof(double) * 10 * (size_t)B);
     A((void**)&w->d_twists, sizeof(double) * 2 * (size_t)B);
     A((void**)&w->d_xy, sizeof(double) * 2 * (size_t)p->n_slots * (size_t)B);
     A((void**)&w->d_truth, sizeof(double) * 3 * (size_t)B);
+    A((void**)&w->d_odom, sizeof(double) * 3 * (size_t)B);
     A((void**)&w->d_vis, (size_t)p->n_slots * (size_t)B);
     if (err == cudaSuccess && n_tubes) err = cudaMemcpyAsync(w->d_tx, tubes_x, sizeof(double) * n_tubes, cudaMemcpyHostToDevice, w->stream);
     if (err == cudaSuccess && n_tubes) err = cudaMemcpyAsync(w->d_ty, tubes_y, sizeof(double) * n_tubes, cudaMemcpyHostToDevice, w->stream);
-    if (err == cudaSuccess) err = cudaMemsetAsync(w->d_robots, 0, sizeof(double) * 7 * (size_t)B, w->stream);
+    if (err == cudaSuccess) err = cudaMemsetAsync(w->d_robots, 0, sizeof(double) * 10 * (size_t)B, w->stream);
     if (err == cudaSuccess) err = cudaStreamSynchronize(w->stream);
     if (err != cudaSuccess) {
         cudaGetLastError();
@@ -314,7 +331,7 @@ int tubeworld_create(int64_t B, const tubeworld_params* p, const double* tubes_x
         return code;
     }
     double* r = w->d_robots;
-    w->R = tw::Robots{r, r + B, r + 2 * B, r + 3 * B, r + 4 * B, r + 5 * B, r + 6 * B};
+    w->R = tw::Robots{r, r + B, r + 2 * B, r + 3 * B, r + 4 * B, r + 5 * B, r + 6 * B, r + 7 * B, r + 8 * B, r + 9 * B};
     *out = w;
     return 0;
 }
@@ -324,7 +341,8 @@ int tubeworld_step_known(tubeworld* w) {
     tw::Dev g(w->device);
     const unsigned blocks = (unsigned)((w->B + 127) / 128);
     tw::k_step_known<<<blocks, 128, 0, w->stream>>>(w->p, w->d_tx, w->d_ty, w->n_tubes, w->seed, w->first_filter, w->B, w->tick,
-                                                   11, w->R, w->calls > 0 ? 1 : 0, w->d_twists, w->d_xy, w->d_vis, w->d_truth);
+                                                   11, w->R, w->calls > 0 ? 1 : 0, w->d_twists, w->d_xy, w->d_vis, w->d_truth,
+                                                   w->d_odom);
     TCU(cudaGetLastError());
     w->tick += 11;
     w->calls += 1;
@@ -344,7 +362,7 @@ int tubeworld_step_scan(tubeworld* w, int ticks, int n_beams) {
     if (ticks > 0) {
         tw::k_advance<<<(unsigned)((w->B + 127) / 128), 128, 0, w->stream>>>(w->p, w->d_tx, w->d_ty, w->n_tubes, w->seed,
                                                                             w->first_filter, w->B, w->tick, ticks, w->R,
-                                                                            w->d_twists, w->d_truth);
+                                                                            w->d_twists, w->d_truth, w->d_odom);
         w->tick += ticks;
     }
     const long long total = w->B * n_beams;
@@ -378,6 +396,17 @@ int tubeworld_download(tubeworld* w, double* twists, double* xy, uint8_t* vis, d
         TCU(cudaMemcpyAsync(ranges, w->d_ranges, sizeof(float) * (size_t)w->n_beams_last * B, cudaMemcpyDeviceToHost, w->stream));
     }
     TCU(cudaStreamSynchronize(w->stream));
+    return 0;
+}
+
+int tubeworld_odometry(tubeworld* w, void** d_odom, double* odom) {
+    if (!w) return tw::fail(-1, "null handle");
+    if (d_odom) *d_odom = w->d_odom;
+    if (odom) {
+        tw::Dev g(w->device);
+        TCU(cudaMemcpyAsync(odom, w->d_odom, sizeof(double) * 3 * (size_t)w->B, cudaMemcpyDeviceToHost, w->stream));
+        TCU(cudaStreamSynchronize(w->stream));
+    }
     return 0;
 }
 

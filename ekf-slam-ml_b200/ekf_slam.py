@@ -44,6 +44,38 @@ def body_twist(wheel_base, wheel_radius, left, right):
     return Twist2D(out[0], Vector2D(out[1], 0.0))
 
 
+def update_pose(wheel_base, wheel_radius, poses, left, right):
+    """DiffDrive::updatePose (diff_drive.cpp:50-67) for a batch of odometers, evaluated by the device twin:
+    poses [count, 3] = {x, y, theta}, wheel angle increments left / right [count] -> new poses."""
+    p = np.array(poses, dtype=np.float64).reshape(-1, 3)
+    l = np.ascontiguousarray(left, dtype=np.float64).reshape(-1)
+    r = np.ascontiguousarray(right, dtype=np.float64).reshape(-1)
+    assert l.size == r.size == p.shape[0]
+    check(_lib.load().ekf_update_pose(float(wheel_base), float(wheel_radius), p.shape[0], p.ctypes.data, l.ctypes.data,
+                                      r.ctypes.data))
+    return p
+
+
+class DiffDrive:
+    """Mirror of rigid2d::DiffDrive's odometry side (diff_drive.hpp:18-60): dead-reckoning pose from wheel angles."""
+
+    def __init__(self, wheel_base, wheel_radius, init_pos=(0.0, 0.0), init_theta=0.0):
+        self.wheel_b, self.wheel_r = float(wheel_base), float(wheel_radius)
+        self._pose = np.array([[init_pos[0], init_pos[1], init_theta]], dtype=np.float64)
+
+    def getBodyTwistForUpdate(self, left_angle, right_angle):
+        return body_twist(self.wheel_b, self.wheel_r, left_angle, right_angle)
+
+    def updatePose(self, left_angle, right_angle):
+        self._pose = update_pose(self.wheel_b, self.wheel_r, self._pose, [left_angle], [right_angle])
+
+    def getPosition(self):
+        return Vector2D(self._pose[0, 0], self._pose[0, 1])
+
+    def getTheta(self):
+        return float(self._pose[0, 2])
+
+
 def normalize_angle(values, device=0):
     """rigid2d::normalize_angle (rigid2d.cpp:336-345) evaluated by the device twin."""
     a = np.ascontiguousarray(values, dtype=np.float64).reshape(-1)

@@ -136,6 +136,10 @@ class TubeWorldSim:
         self.x = np.zeros(B)
         self.y = np.zeros(B)
         self.th = np.zeros(B)
+        # dead-reckoning odometer (slam.cpp:96): integrates the same wheel increments, never sees a collision
+        self.ox = np.zeros(B)
+        self.oy = np.zeros(B)
+        self.oth = np.zeros(B)
         self.tick = 0
         self.v = np.zeros(B)
         self.om = np.zeros(B)
@@ -169,6 +173,10 @@ class TubeWorldSim:
         self.x = self.x + c * bx - s * by
         self.y = self.y + s * bx + c * by
         self.th = self.th + dth
+        co, so = np.cos(self.oth), np.sin(self.oth)
+        self.ox = self.ox + co * bx - so * by
+        self.oy = self.oy + so * bx + co * by
+        self.oth = self.oth + dth
         # collision: first tube closer than radius + wheel_base/2 snaps the robot back, :316-366
         lim = w.tube_radius + w.wheel_base / 2
         dx = w.tubes_x[None, :] - self.x[:, None]
@@ -272,7 +280,7 @@ def simulate_known(world: World, B: int, steps: int, seed: int = 0, first_filter
 
     Returns dict of time-major arrays: twists [T,B,2] (dtheta, dx), xy [T,B,2*n_slots],
     vis [T,B,n_slots] uint8 (all zero at step 0: the node's first measurement() call only initialises,
-    slam.cpp:315-327), truth [T,B,3] (x, y, theta)."""
+    slam.cpp:315-327), truth [T,B,3] (x, y, theta), odom [T,B,3] (the dead-reckoning pose of slam.cpp:96)."""
     if workers > 1 and B >= 4 * workers:
         return _parallel(simulate_known, world, B, steps, seed, first_filter, workers)
     sim = TubeWorldSim(world, B, seed, first_filter)
@@ -281,9 +289,11 @@ def simulate_known(world: World, B: int, steps: int, seed: int = 0, first_filter
     xy = np.zeros((steps, B, 2 * n))
     vis = np.zeros((steps, B, n), dtype=np.uint8)
     truth = np.zeros((steps, B, 3))
+    odom = np.zeros((steps, B, 3))
     for t in range(steps):
         for _ in range(11):
             sim.step_tick()
+        odom[t, :, 0], odom[t, :, 1], odom[t, :, 2] = sim.ox, sim.oy, sim.oth
         rx, ry, v = sim.fake_sensor()
         dth, dx = sim.odom_twist()
         tw[t, :, 0], tw[t, :, 1] = dth, dx
@@ -292,7 +302,7 @@ def simulate_known(world: World, B: int, steps: int, seed: int = 0, first_filter
         if t > 0:
             vis[t, :, :nt] = v[:, :nt]
         truth[t, :, 0], truth[t, :, 1], truth[t, :, 2] = sim.x, sim.y, sim.th
-    return {"twists": tw, "xy": xy, "vis": vis, "truth": truth}
+    return {"twists": tw, "xy": xy, "vis": vis, "truth": truth, "odom": odom}
 
 
 def simulate_unknown(world: World, B: int, steps: int, seed: int = 0, first_filter: int = 0, m_max=None,

@@ -65,7 +65,9 @@ class TubeWorld:
         _check(self._L.tubeworld_download(self._h, tw.ctypes.data_as(c_double_p), xy.ctypes.data_as(c_double_p),
                                           vis.ctypes.data_as(c_u8_p), truth.ctypes.data_as(c_double_p),
                                           rg.ctypes.data_as(c_float_p) if ranges else None))
-        out = {"twists": tw, "xy": xy, "vis": vis, "truth": truth}
+        odom = np.empty((self.B, 3))
+        _check(self._L.tubeworld_odometry(self._h, None, odom.ctypes.data))
+        out = {"twists": tw, "xy": xy, "vis": vis, "truth": truth, "odom": odom}
         if ranges:
             out["ranges"] = rg
         return out

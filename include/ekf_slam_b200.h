@@ -161,6 +161,12 @@ int ekf_normalize_angles(const double* in, double* out, int64_t count, int devic
 /* DiffDrive::getBodyTwistForUpdate(left, right) -> out2 = {angular, linear_x}
  *                                                               rigid2d/src/diff_drive.cpp:38-47 */
 int ekf_body_twist(double wheel_base, double wheel_radius, double left, double right, double* out2);
+/* DiffDrive::updatePose for `count` independent odometers (rigid2d/src/diff_drive.cpp:50-67 with integrateTwist,
+ * rigid2d/src/rigid2d.cpp:304-333, and the acos / asin rotation of Transform2D::operator*=, :222-245):
+ * poses [count][3] = {x, y, theta} are advanced in place by the wheel angle increments left / right [count].
+ * HOST buffers; theta is not wrapped (as in the reference). */
+int ekf_update_pose(double wheel_base, double wheel_radius, int64_t count, double* poses, const double* left,
+                    const double* right);
 
 #ifdef __cplusplus
 }

@@ -40,6 +40,10 @@ int tubeworld_step_scan(tubeworld* w, int ticks, int n_beams);
 int tubeworld_outputs(tubeworld* w, void** d_twists, void** d_xy, void** d_vis, void** d_truth, void** d_ranges);
 /* host copies of the same (any pointer may be NULL) */
 int tubeworld_download(tubeworld* w, double* twists, double* xy, uint8_t* vis, double* truth, float* ranges);
+/* The dead-reckoning odometer the SLAM node runs beside the filter (nuslam/src/slam.cpp:96: DiffDrive::updatePose on
+ * every joint_states message): the same wheel increments as the truth, no collision handling.  odom [B][3] = {x, y,
+ * theta}; d_odom receives the device pointer, odom (host, optional) a copy; either may be NULL. */
+int tubeworld_odometry(tubeworld* w, void** d_odom, double* odom);
 int tubeworld_sync(tubeworld* w);
 void* tubeworld_stream(tubeworld* w);
 /* run on the consumer's CUDA stream (e.g. ekf_batch_stream()) so that sim -> filter is stream-ordered */

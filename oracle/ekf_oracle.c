@@ -46,6 +46,53 @@ void oracle_body_twist(double wheel_base, double wheel_radius, double left, doub
     out2[1] = (r / 2.0) * (right + left);
 }
 
+/* Transform2D::operator*=, rigid2d.cpp:222-245: the composed rotation goes through acos / asin (kept as written:
+ * a negative rotation beyond -pi/2 comes out wrong in the reference, and small ones carry acos' cancellation). */
+static void compose_tf(double ax, double ay, double ath, double bx, double by, double bth, double* ox, double* oy,
+                       double* oth) {
+    double r11 = (cos(ath) * cos(bth)) - (sin(ath) * sin(bth));
+    double r21 = (sin(ath) * cos(bth)) + (cos(ath) * sin(bth));
+    double rc = acos(r11), rs = asin(r21);
+    double rot = rc;
+    if ((rc * rs) < 0) rot = rs;
+    double cx = bx * cos(ath) - by * sin(ath) + ax;
+    double cy = bx * sin(ath) + by * cos(ath) + ay;
+    *ox = cx;
+    *oy = cy;
+    *oth = rot;
+}
+
+/* integrateTwist, rigid2d.cpp:304-333; out = {x, y, theta} of T_bb' */
+void oracle_integrate_twist(double w, double vx, double vy, double* out3) {
+    if (fabs(w) > 0.0001) {
+        double xs = vy / w, ys = -vx / w;
+        /* t_sb = (xs, ys, 0); t_bs = t_sb.inv() (rigid2d.cpp:208-217) */
+        double bsx = -xs * cos(0.0) - ys * sin(0.0), bsy = xs * sin(0.0) - ys * cos(0.0), bsth = -0.0;
+        double t1x, t1y, t1th;
+        compose_tf(0.0, 0.0, w, xs, ys, 0.0, &t1x, &t1y, &t1th); /* t_ssq * t_sqbq */
+        compose_tf(bsx, bsy, bsth, t1x, t1y, t1th, &out3[0], &out3[1], &out3[2]);
+    } else {
+        out3[0] = vx;
+        out3[1] = vy;
+        out3[2] = 0.0;
+    }
+}
+
+/* DiffDrive::updatePose, diff_drive.cpp:50-67; pose = {x, y, theta} in place (theta is not wrapped) */
+void oracle_update_pose(double wheel_base, double wheel_radius, double* pose3, double left, double right) {
+    double tw[2], t[3];
+    oracle_body_twist(wheel_base, wheel_radius, left, right, tw);
+    oracle_integrate_twist(tw[0], tw[1], 0.0, t);
+    /* q = Transform2D(theta).adjConvert(Twist2D(t.theta, (t.x, t.y))), rigid2d.cpp:262-274 with zero translation */
+    double th = pose3[2];
+    double qa = t[2];
+    double qx = qa * 0.0 + t[0] * cos(th) - t[1] * sin(th);
+    double qy = -qa * 0.0 + t[0] * sin(th) + t[1] * cos(th);
+    pose3[0] += qx;
+    pose3[1] += qy;
+    pose3[2] += qa;
+}
+
 /* ekf_slam.cpp:27-53 */
 ekf_oracle_t* oracle_create(int n) {
     ekf_oracle_t* o = (ekf_oracle_t*)calloc(1, sizeof(*o));

@@ -123,6 +123,13 @@ void ref_body_twist(double wheel_base, double wheel_radius, double dl, double dr
     out2[1] = t.linearX();
 }
 
+void ref_integrate_twist(double w, double vx, double vy, double* out3) {
+    rigid2d::Transform2D t = rigid2d::integrateTwist(rigid2d::Twist2D(w, rigid2d::Vector2D(vx, vy)));
+    out3[0] = t.x();
+    out3[1] = t.y();
+    out3[2] = t.theta();
+}
+
 void ref_wheel_velocity(double wheel_base, double wheel_radius, double ang, double vx, double* out2) {
     rigid2d::DiffDrive dd(wheel_base, wheel_radius);
     rigid2d::Vector2D w = dd.calculateWheelVelocity(rigid2d::Twist2D(ang, rigid2d::Vector2D(vx, 0.0)));

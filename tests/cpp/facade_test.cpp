@@ -52,6 +52,12 @@ int main() {
     copy.prediction(Twist2D(0.1, Vector2D(0.05, 0.0)));
     REQUIRE(std::fabs(copy.getStateTheta() - slam_agent.getStateTheta()) > 0.05);
 
+    // --- the odometer the node runs beside the filter (slam.cpp:96), known answer of rigid2d/tests/tests.cpp:372-383
+    DiffDrive odo(0.2, 0.05);
+    odo.updatePose(0.0, 2 * 3.1415926);
+    REQUIRE(std::fabs(odo.getTheta() - 1.5708) < 2e-5);
+    REQUIRE(std::fabs(odo.getPosition().x - 0.1) < 2e-6 && std::fabs(odo.getPosition().y - 0.1) < 2e-6);
+
     // --- unknown data association pattern
     EKF_SLAM uda(20);
     std::vector<bool> known_list(20, false);

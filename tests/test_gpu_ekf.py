@@ -162,6 +162,36 @@ def test_normalize_angle_device_twin_is_bit_exact(gpu_pkg):
     np.testing.assert_allclose(g, [0.523599, -2.26893, 0.523599], rtol=1.2e-5)
 
 
+def test_update_pose_device_twin(gpu_pkg):
+    """DiffDrive::updatePose on the device vs the pinned C restatement (CUDA sincos / acos / asin differ from libm in
+    the last bits, and acos amplifies them for small rotations: 1e-9 absolute) + the reference's known answers."""
+    import ctypes
+    from _oracle import oracle_lib
+    L = oracle_lib()
+    d, P = ctypes.c_double, ctypes.POINTER(ctypes.c_double)
+    rng = np.random.default_rng(9)
+    n = 5000
+    poses = np.column_stack([rng.normal(size=n), rng.normal(size=n), rng.uniform(-7, 7, size=n)])
+    left, right = rng.uniform(-0.2, 0.2, size=n), rng.uniform(-0.2, 0.2, size=n)
+    left[::3], right[::3] = rng.uniform(-40, 40, size=len(left[::3])), rng.uniform(-40, 40, size=len(left[::3]))
+    right[::7] = left[::7] + rng.uniform(-1e-6, 1e-6, size=len(left[::7]))
+    got = gpu_pkg.update_pose(0.16, 0.033, poses, left, right)
+    want = poses.copy()
+    for k in range(n):
+        L.oracle_update_pose(d(0.16), d(0.033), want[k].ctypes.data_as(P), d(left[k]), d(right[k]))
+    np.testing.assert_allclose(got, want, rtol=0, atol=1e-9)
+    # rigid2d/tests/tests.cpp:334-383
+    dd = gpu_pkg.DiffDrive(0.2, 0.01)
+    dd.updatePose(0.5, 0.5)
+    assert abs(dd.getPosition().x - 0.005) < 1e-7 and abs(dd.getPosition().y) < 1e-12
+    dd = gpu_pkg.DiffDrive(0.2, 0.01)
+    dd.updatePose(-15.7, 15.7)
+    assert abs(dd.getTheta() - 1.57) < 2e-5 and abs(dd.getPosition().x) < 1e-12
+    dd = gpu_pkg.DiffDrive(0.2, 0.05)
+    dd.updatePose(0.0, 2 * 3.1415926)
+    assert abs(dd.getTheta() - 1.5708) < 2e-5 and abs(dd.getPosition().x - 0.1) < 2e-6 and abs(dd.getPosition().y - 0.1) < 2e-6
+
+
 def test_batch_matches_per_filter_oracle(gpu_pkg):
     """cfg3 in miniature: every filter of a batch equals its own oracle run (known association)."""
     tg = gpu_pkg.tracegen

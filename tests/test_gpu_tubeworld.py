@@ -18,11 +18,22 @@ def test_known_association_inputs_match_tracegen(gpu_pkg):
         d = sim.download()
         np.testing.assert_allclose(d["twists"], ref["twists"][t], rtol=0, atol=1e-12)
         np.testing.assert_allclose(d["truth"], ref["truth"][t], rtol=0, atol=1e-9)
+        np.testing.assert_allclose(d["odom"], ref["odom"][t], rtol=0, atol=1e-9)
         np.testing.assert_allclose(d["xy"], ref["xy"][t], rtol=0, atol=1e-9)
         dist = np.hypot(w.tubes_x[None, :] - ref["truth"][t][:, 0:1], w.tubes_y[None, :] - ref["truth"][t][:, 1:2])
         clear = np.abs(dist - w.max_visible) > 1e-6
         assert np.array_equal(d["vis"][:, :20][clear], ref["vis"][t][:, :20][clear])
     assert ref["vis"][1:].sum() > 1000
+    # The odometer integrates the truth's own wheel increments: it equals the truth until the first collision, and
+    # the reference's DiffDrive::updatePose (device twin, acos / asin composition) follows the same path.
+    free = np.all(np.abs(ref["odom"][-1] - ref["truth"][-1]) < 1e-12, axis=1)
+    assert free.any()
+    sim1 = tg.TubeWorldSim(w, 4, seed=12, first_filter=first)
+    poses = np.zeros((4, 3))
+    for _ in range(60):
+        sim1.step_tick()
+        poses = gpu_pkg.update_pose(w.wheel_base, w.wheel_radius, poses, sim1.dl, sim1.dr)
+    np.testing.assert_allclose(poses, np.column_stack([sim1.ox, sim1.oy, sim1.oth]), rtol=0, atol=1e-9)
 
 
 def test_batch_independence_and_scan(gpu_pkg):

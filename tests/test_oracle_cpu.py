@@ -146,6 +146,36 @@ def test_normalize_angle_and_twist_goldens():
         assert np.array_equal(out, t)
 
 
+def test_odometry_restatement_is_pinned():
+    """DiffDrive::updatePose / integrateTwist: the C restatement equals the reference build bit for bit (same libm),
+    incl. the acos / asin rotation of Transform2D::operator*=, and reproduces the reference's own known answers
+    (rigid2d/tests/tests.cpp:285-318 integrateTwist, :334-383 updatePose; Catch Approx = relative 1.2e-5)."""
+    L, R = oracle_lib(), ref_lib()
+    d, P = ctypes.c_double, ctypes.POINTER(ctypes.c_double)
+    rng = np.random.default_rng(5)
+    for k in range(4000):
+        pose = np.array([rng.normal(), rng.normal(), rng.uniform(-7, 7)])
+        l, r = (rng.uniform(-0.2, 0.2), rng.uniform(-0.2, 0.2)) if k % 3 else (rng.uniform(-40, 40), rng.uniform(-40, 40))
+        if k % 7 == 0:
+            r = l + rng.uniform(-1e-6, 1e-6)  # below the 1e-4 rad "straight line" threshold
+        a, b = pose.copy(), pose.copy()
+        L.oracle_update_pose(d(0.16), d(0.033), a.ctypes.data_as(P), d(l), d(r))
+        R.ref_update_pose(d(0.16), d(0.033), b.ctypes.data_as(P), d(l), d(r))
+        assert np.array_equal(a, b), (pose, l, r)
+    t = np.zeros(3)
+    for (w, vx, vy), want in (((0.0, 1.0, 2.0), (1.0, 2.0, 0.0)), ((0.5, 0.0, 0.0), (0.0, 0.0, 0.5)),
+                              ((0.5, 1.0, 2.2), (0.4202143, 2.3543072, 0.5))):
+        L.oracle_integrate_twist(d(w), d(vx), d(vy), t.ctypes.data_as(P))
+        assert np.allclose(t, want, rtol=1.2e-5, atol=1e-12)
+    for (wb, wr, l, r), want in (((0.2, 0.01, 0.5, 0.5), (0.005, 0.0, None)), ((0.2, 0.01, -0.5, -0.5), (-0.005, 0.0, None)),
+                                 ((0.2, 0.01, -15.7, 15.7), (0.0, 0.0, 1.57)),
+                                 ((0.2, 0.05, 0.0, 2 * 3.1415926), (0.1, 0.1, 1.5708))):
+        a = np.zeros(3)
+        L.oracle_update_pose(d(wb), d(wr), a.ctypes.data_as(P), d(l), d(r))
+        for got, w_ in zip(a, want):
+            assert w_ is None or abs(got - w_) <= 1.2e-5 * max(abs(w_), 1e-7) + 1e-12
+
+
 # ---------------------------------------------------------------- circle fitting oracle
 GOLD_RANGES = [0.713136, 0.682084, 0.668864, 0.660664, 0.65551, 0.652665, 0.651814, 0.652875, 0.655952, 0.661391,
                0.670004, 0.684042, 1.01247, 1.01543, 1.01872, 1.02234, 1.0263, 1.03061, 1.04061, 1.05061, 1.06061]
