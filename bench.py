@@ -242,8 +242,8 @@ def large_map_leg(pkg, device, n_lm, timed_updates, peak_gbs, want_cpu):
 
 
 def sharded_map_leg(pkg, dist, local, n_lm, timed_updates, peak_gbs):
-    """cfg5: one filter, n_lm landmarks, Sigma row-block-sharded over all ranks (NCCL all-reduce of W and all-gather
-    of K per correction).  Timed on the device, max over ranks."""
+    """cfg5: one filter, n_lm landmarks, Sigma row-block-sharded over all ranks (one NCCL all-reduce of W per
+    correction; K is formed locally on every rank).  Timed on the device, max over ranks."""
     from ekf_slam_ml_b200.sharded import ShardedEKF
     tg = pkg.tracegen
     world = dist.get_world_size()
@@ -277,7 +277,7 @@ def sharded_map_leg(pkg, dist, local, n_lm, timed_updates, peak_gbs):
     per_gpu_bytes = 16.0 * N * N / world
     out = {
         "workload": f"cfg5: single map, n={n_lm} landmarks (N={N}, Sigma {8.0 * N * N / 1e9:.1f} GB) row-block-sharded over "
-                    f"{world} GPUs; per correction: NCCL all-reduce of W (2N fp64) + all-gather of K (2N fp64), sweep of own rows",
+                    f"{world} GPUs; per correction: one NCCL all-reduce of W (2N fp64), K = W^T S^-1 formed on every rank, sweep of own rows",
         "value": 1e3 / ms_upd, "unit": UNIT, "updates_timed": done, "ms_per_update": ms_upd,
         "gpu_launches_rank0": int(f.launch_count - (l0 or 0)), "rows_rank0": list(rows),
         "roofline": {"bound": "hbm", "kernel": "k_large_sweep_p<P> on each rank's rows (time per sweep = whole step incl. "

@@ -149,60 +149,44 @@ __global__ void __launch_bounds__(256)
     Wpart[c] = w;  // a dropped measurement contributes a zero factor
 }
 
-__global__ void k_sh_ctx_s(const double2* __restrict__ W2, Ctx* __restrict__ ctx) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    if (!ctx->active) return;
-    const Hj h = ctx->h;
-    const int i3 = ctx->i3;
-    const double2 w0 = W2[0], w1 = W2[1], w2 = W2[2], w3 = W2[i3], w4 = W2[i3 + 1];
-    const double s00 = h_row0(h, w1.x, w2.x, w3.x, w4.x) + kR;
-    const double s01 = h_row1(h, w0.x, w1.x, w2.x, w3.x, w4.x);
-    const double s10 = h_row0(h, w1.y, w2.y, w3.y, w4.y);
-    const double s11 = h_row1(h, w0.y, w1.y, w2.y, w3.y, w4.y) + kR;
-    ctx->si = inv2x2(s00, s01, s10, s11);
-    ctx->nu0 = __dsub_rn(ctx->zr, h.zr);
-    ctx->nu1 = normalize_angle(__dsub_rn(ctx->zphi, h.zphi));
-}
-
-// K rows of this shard: K[r] = (Sigma_current[r, idx] Hj^T) S^-1, written into factor slot p
+// After the all-reduce every rank holds the full W = Hj Sigma.  With Sigma symmetric (kept to rounding by the
+// reference's (I - K H) Sigma) K = Sigma Hj^T S^-1 = W^T S^-1, so every replica forms ALL of K and the
+// state update locally: no strided column reads of the local rows and no exchange of K.
 __global__ void __launch_bounds__(256)
-    k_sh_gain(const double* __restrict__ sig_local, long long ld, long long r0, int rows, const Ctx* __restrict__ ctx,
-              double2* __restrict__ Kp, const double2* __restrict__ Wp, int p) {
-    const int lr = blockIdx.x * blockDim.x + threadIdx.x;
-    if (lr >= rows) return;
-    double2* Kout = Kp + (long long)p * ld;
-    if (!ctx->active) {
-        Kout[r0 + lr] = make_double2(0.0, 0.0);
+    k_sh_gain_state(const double2* __restrict__ Wp_slot, double2* __restrict__ Kout, double* __restrict__ state,
+                    const Ctx* __restrict__ ctx, int N, long long ld) {
+    __shared__ Sym2 si_s;
+    __shared__ double nu_s[2];
+    __shared__ int active_s;
+    if (threadIdx.x == 0) {
+        active_s = ctx->active;
+        if (active_s) {
+            const Hj h = ctx->h;
+            const int i3 = ctx->i3;
+            const double2 w0 = Wp_slot[0], w1 = Wp_slot[1], w2 = Wp_slot[2], w3 = Wp_slot[i3], w4 = Wp_slot[i3 + 1];
+            const double s00 = h_row0(h, w1.x, w2.x, w3.x, w4.x) + kR;
+            const double s01 = h_row1(h, w0.x, w1.x, w2.x, w3.x, w4.x);
+            const double s10 = h_row0(h, w1.y, w2.y, w3.y, w4.y);
+            const double s11 = h_row1(h, w0.y, w1.y, w2.y, w3.y, w4.y) + kR;
+            si_s = inv2x2(s00, s01, s10, s11);
+            nu_s[0] = __dsub_rn(ctx->zr, h.zr);
+            nu_s[1] = normalize_angle(__dsub_rn(ctx->zphi, h.zphi));
+        }
+    }
+    __syncthreads();
+    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= ld) return;
+    if (k >= N || !active_s) {
+        Kout[k] = make_double2(0.0, 0.0);
         return;
     }
-    const Hj h = ctx->h;
-    const Sym2 si = ctx->si;
-    const int i3 = ctx->i3;
-    const double* row = sig_local + (long long)lr * ld;
-    double q0 = row[0], q1 = row[1], q2 = row[2], q3 = row[i3], q4 = row[i3 + 1];
-    for (int j = 0; j < p; ++j) {
-        const double2 kj = Kp[(long long)j * ld + r0 + lr];
-        const double2* wj = Wp + (long long)j * ld;
-        q0 = apply_factor(q0, kj, wj[0]);
-        q1 = apply_factor(q1, kj, wj[1]);
-        q2 = apply_factor(q2, kj, wj[2]);
-        q3 = apply_factor(q3, kj, wj[i3]);
-        q4 = apply_factor(q4, kj, wj[i3 + 1]);
-    }
-    const double p0 = h_row0(h, q1, q2, q3, q4), p1 = h_row1(h, q0, q1, q2, q3, q4);
-    Kout[r0 + lr] = make_double2(fma(p1, si.i10, p0 * si.i00), fma(p1, si.i11, p0 * si.i01));
-}
-
-// every replica applies the same state update from the gathered K
-__global__ void __launch_bounds__(256)
-    k_sh_state(double* __restrict__ state, const double2* __restrict__ K2, const Ctx* __restrict__ ctx, int N) {
-    const int r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= N) return;
-    if (!ctx->active) return;
-    const double2 k = K2[r];
-    double ns = state[r] + fma(k.y, ctx->nu1, k.x * ctx->nu0);
-    if (r == 0) ns = normalize_angle(ns);
-    state[r] = ns;
+    const double2 w = Wp_slot[k];
+    const Sym2 si = si_s;
+    const double k0 = fma(w.y, si.i10, w.x * si.i00), k1 = fma(w.y, si.i11, w.x * si.i01);
+    Kout[k] = make_double2(k0, k1);
+    double ns = state[k] + fma(k1, nu_s[1], k0 * nu_s[0]);
+    if (k == 0) ns = normalize_angle(ns);  // ekf_slam.cpp:187
+    state[k] = ns;
 }
 
 // ---- association
@@ -465,7 +449,7 @@ int ensure_m(ekf_sharded* h, int m) {
     return 0;
 }
 
-// ---- the three exchanges
+// ---- the exchanges
 int exchange_W(ekf_sharded* h) {
     if (h->local) {
         const int g = (int)((h->ld + 255) / 256);
@@ -478,26 +462,6 @@ int exchange_W(ekf_sharded* h) {
         Shard& s = h->sh[0];
         NC(ncclAllReduce(s.Wpart, s.W2 + (long long)h->pending * h->ld, 2 * (size_t)h->ld, ncclDouble, ncclSum, h->comm,
                          h->stream));
-    }
-    return 0;
-}
-int exchange_K(ekf_sharded* h) {
-    const long long off = (long long)h->pending * h->ld;  // factor slot being filled
-    if (h->local) {
-        for (auto& src : h->sh)
-            for (auto& dst : h->sh)
-                if (&src != &dst && src.rows > 0)
-                    CU(cudaMemcpyAsync(dst.K2 + off + src.r0, src.K2 + off + src.r0, sizeof(double2) * src.rows,
-                                       cudaMemcpyDeviceToDevice, h->stream));
-    } else {
-        Shard& s = h->sh[0];
-        NC(ncclGroupStart());
-        for (int g = 0; g < h->world; ++g) {
-            const long long r0 = h->r0_of[g], rows = h->r1_of[g] - r0;
-            if (rows > 0)
-                NC(ncclBroadcast(s.K2 + off + r0, s.K2 + off + r0, 2 * (size_t)rows, ncclDouble, g, h->comm, h->stream));
-        }
-        NC(ncclGroupEnd());
     }
     return 0;
 }
@@ -550,15 +514,8 @@ int correct(ekf_sharded* h, bool use_cmd, bool stale_pose, int lm, double sx, do
     int rc = exchange_W(h);
     if (rc) return rc;
     for (auto& s : h->sh) {
-        k_sh_ctx_s<<<1, 32, 0, h->stream>>>(s.W2 + (long long)p * h->ld, s.ctx);
-        if (s.rows > 0) k_sh_gain<<<(s.rows + 255) / 256, 256, 0, h->stream>>>(s.sig, h->ld, s.r0, s.rows, s.ctx, s.K2, s.W2, p);
-        h->launches += 2;
-    }
-    CU(cudaGetLastError());
-    rc = exchange_K(h);
-    if (rc) return rc;
-    for (auto& s : h->sh) {
-        k_sh_state<<<(h->N + 255) / 256, 256, 0, h->stream>>>(s.state, s.K2 + (long long)p * h->ld, s.ctx, h->N);
+        k_sh_gain_state<<<gl, 256, 0, h->stream>>>(s.W2 + (long long)p * h->ld, s.K2 + (long long)p * h->ld, s.state, s.ctx,
+                                                   h->N, h->ld);
         h->launches += 1;
     }
     CU(cudaGetLastError());

@@ -6,8 +6,8 @@
  * Partition: rank g owns the rows of landmarks [L_g, L_g+1) (two rows each, never split) and rank 0 additionally
  * the three robot rows; every rank holds all N columns of its rows, a replica of the state vector, and runs the
  * rank-2 sweep on its own rows only.  Per correction the ranks exchange
- *   W = Hj*Sigma (2 x N): all-reduce of the owners' partial products (reference-faithful: W comes from ROWS), and
- *   K (N x 2): all-gather of the row slices (so that every replica applies the same state update);
+ *   W = Hj*Sigma (2 x N): all-reduce of the owners' partial products (W comes from ROWS, as in the reference);
+ *   every replica then forms K = W^T S^-1 (Sigma symmetric) and the state update locally, so K is not exchanged;
  * per associated measurement additionally the 3 x N robot rows (broadcast from rank 0) and one 24-byte
  * (distance, runner-up, index) triple per rank.
  */
