@@ -629,6 +629,7 @@ def main():
     ap.add_argument("--large-updates", type=int, default=200)
     ap.add_argument("--skip-large", action="store_true")
     ap.add_argument("--only-large", action="store_true", help="profiling aid: run just the cfg4 leg")
+    ap.add_argument("--only-laser", action="store_true", help="profiling aid: run just the laser front-end leg")
     ap.add_argument("--sharded-n", type=int, default=40000, help="cfg5 landmarks (square number), N>1 only")
     ap.add_argument("--sharded-updates", type=int, default=50)
     args = ap.parse_args()
@@ -637,6 +638,9 @@ def main():
     elif args.only_large:
         import ekf_slam_ml_b200 as pkg
         print(json.dumps(large_map_leg(pkg, 0, args.large_n, args.large_updates, measured_peaks()[0], want_cpu=False)))
+    elif args.only_laser:
+        import ekf_slam_ml_b200 as pkg
+        print(json.dumps(laser_leg(pkg, 0)))
     else:
         run_ours(args)
 
