@@ -71,6 +71,11 @@ SIGNATURES = {
     "ekf_batch_get_poses_async": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
     "ekf_batch_get_states": (ctypes.c_int, [ctypes.c_void_p, c_double_p]),
     "ekf_batch_get_sigma": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, c_double_p, ctypes.c_int64]),
+    "ekf_batch_checkpoint_size": (ctypes.c_int, [ctypes.c_void_p, c_i64_p, c_i64_p]),
+    "ekf_batch_export": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                        ctypes.c_void_p, ctypes.c_void_p]),
+    "ekf_batch_import": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                        ctypes.c_void_p, ctypes.c_uint64]),
     "ekf_batch_get_known": (ctypes.c_int, [ctypes.c_void_p, c_u8_p]),
     "ekf_batch_set_known": (ctypes.c_int, [ctypes.c_void_p, c_u8_p]),
     "ekf_batch_update_count": (ctypes.c_int, [ctypes.c_void_p, c_u64_p]),

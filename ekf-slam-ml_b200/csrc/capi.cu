@@ -1118,6 +1118,46 @@ int ekf_batch_get_known(ekf_batch* b, uint8_t* out) {
     CU(cudaStreamSynchronize(b->stream));
     return EKF_OK;
 }
+// Checkpoint / resume of the whole batch: the arrays exactly as the engine keeps them (Sigma in its packed symmetric
+// layout, per-filter strides as reported by ekf_batch_checkpoint_size).  No conversion, so a restored batch continues
+// bit-identically.
+int ekf_batch_checkpoint_size(ekf_batch* b, int64_t* sigma_doubles, int64_t* state_doubles) {
+    if (!b) return fail(EKF_ERR_INVALID, "null handle");
+    if (sigma_doubles) *sigma_doubles = (int64_t)b->sig_stride * b->B;
+    if (state_doubles) *state_doubles = (int64_t)b->st_stride * b->B;
+    return EKF_OK;
+}
+int ekf_batch_export(ekf_batch* b, double* sigma, double* state, int32_t* init_flag, uint8_t* known, uint64_t* updates) {
+    if (!b || !sigma || !state || !init_flag || !known) return fail(EKF_ERR_INVALID, "null argument");
+    DeviceGuard g(b->device);
+    const size_t B = (size_t)b->B;
+    CU(cudaStreamSynchronize(b->copy_stream));
+    CU(cudaMemcpyAsync(sigma, b->d_sigma, sizeof(double) * b->sig_stride * B, cudaMemcpyDeviceToHost, b->stream));
+    CU(cudaMemcpyAsync(state, b->d_state, sizeof(double) * b->st_stride * B, cudaMemcpyDeviceToHost, b->stream));
+    CU(cudaMemcpyAsync(init_flag, b->d_init_flag, sizeof(int32_t) * B, cudaMemcpyDeviceToHost, b->stream));
+    CU(cudaMemcpyAsync(known, b->d_known, (size_t)b->n * B, cudaMemcpyDeviceToHost, b->stream));
+    unsigned long long u = 0;
+    CU(cudaMemcpyAsync(&u, b->d_nupd, sizeof(u), cudaMemcpyDeviceToHost, b->stream));
+    CU(cudaStreamSynchronize(b->stream));
+    if (updates) *updates = (uint64_t)u;
+    return EKF_OK;
+}
+int ekf_batch_import(ekf_batch* b, const double* sigma, const double* state, const int32_t* init_flag,
+                     const uint8_t* known, uint64_t updates) {
+    if (!b || !sigma || !state || !init_flag || !known) return fail(EKF_ERR_INVALID, "null argument");
+    DeviceGuard g(b->device);
+    const size_t B = (size_t)b->B;
+    CU(cudaStreamSynchronize(b->copy_stream));
+    CU(cudaStreamSynchronize(b->out_stream));
+    CU(cudaMemcpyAsync(b->d_sigma, sigma, sizeof(double) * b->sig_stride * B, cudaMemcpyHostToDevice, b->stream));
+    CU(cudaMemcpyAsync(b->d_state, state, sizeof(double) * b->st_stride * B, cudaMemcpyHostToDevice, b->stream));
+    CU(cudaMemcpyAsync(b->d_init_flag, init_flag, sizeof(int32_t) * B, cudaMemcpyHostToDevice, b->stream));
+    CU(cudaMemcpyAsync(b->d_known, known, (size_t)b->n * B, cudaMemcpyHostToDevice, b->stream));
+    const unsigned long long u = (unsigned long long)updates;
+    CU(cudaMemcpyAsync(b->d_nupd, &u, sizeof(u), cudaMemcpyHostToDevice, b->stream));
+    CU(cudaStreamSynchronize(b->stream));
+    return EKF_OK;
+}
 int ekf_batch_set_known(ekf_batch* b, const uint8_t* in) {
     if (!b || !in) return fail(EKF_ERR_INVALID, "null argument");
     DeviceGuard g(b->device);

@@ -403,6 +403,41 @@ class EKFBatch:
         check(self._L.ekf_batch_timer_stop(self._h, ctypes.byref(ms)))
         return ms.value
 
+    def checkpoint(self):
+        """Everything needed to resume the batch bit-identically (dict of numpy arrays; Sigma in the engine's packed
+        symmetric layout).  save_checkpoint / load_checkpoint put it in an .npz file."""
+        ns, nst = ctypes.c_int64(), ctypes.c_int64()
+        check(self._L.ekf_batch_checkpoint_size(self._h, ctypes.byref(ns), ctypes.byref(nst)))
+        ck = {"sigma_packed": np.empty(ns.value), "state": np.empty(nst.value),
+              "init_flag": np.empty(self.B, dtype=np.int32), "known": np.empty((self.B, self.n), dtype=np.uint8)}
+        upd = ctypes.c_uint64()
+        check(self._L.ekf_batch_export(self._h, ck["sigma_packed"].ctypes.data, ck["state"].ctypes.data,
+                                       ck["init_flag"].ctypes.data, ck["known"].ctypes.data, ctypes.byref(upd)))
+        ck["updates"] = np.uint64(upd.value)
+        ck["shape"] = np.array([self.B, self.n], dtype=np.int64)
+        return ck
+
+    def restore(self, ck):
+        if tuple(int(v) for v in ck["shape"]) != (self.B, self.n):
+            raise ValueError("checkpoint is for a batch of another shape")
+        ns, nst = ctypes.c_int64(), ctypes.c_int64()
+        check(self._L.ekf_batch_checkpoint_size(self._h, ctypes.byref(ns), ctypes.byref(nst)))
+        sig = np.ascontiguousarray(ck["sigma_packed"], dtype=np.float64)
+        st = np.ascontiguousarray(ck["state"], dtype=np.float64)
+        fl = np.ascontiguousarray(ck["init_flag"], dtype=np.int32)
+        kn = np.ascontiguousarray(ck["known"], dtype=np.uint8)
+        if sig.size != ns.value or st.size != nst.value or fl.size != self.B or kn.size != self.B * self.n:
+            raise ValueError("checkpoint arrays do not match this build's layout")
+        check(self._L.ekf_batch_import(self._h, sig.ctypes.data, st.ctypes.data, fl.ctypes.data, kn.ctypes.data,
+                                       int(ck["updates"])))
+
+    def save_checkpoint(self, path):
+        np.savez(path, **self.checkpoint())
+
+    def load_checkpoint(self, path):
+        with np.load(path) as z:
+            self.restore({k: z[k] for k in z.files})
+
     def device_pointers(self):
         s, st = ctypes.c_void_p(), ctypes.c_void_p()
         ss, sts = ctypes.c_int64(), ctypes.c_int64()

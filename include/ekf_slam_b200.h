@@ -137,6 +137,14 @@ int ekf_batch_get_sigma(ekf_batch* b, int64_t filter, double* out, int64_t ld);
 int ekf_batch_get_known(ekf_batch* b, uint8_t* out /* [B][n] */);
 int ekf_batch_set_known(ekf_batch* b, const uint8_t* in);
 int ekf_batch_update_count(ekf_batch* b, uint64_t* out);
+/* Checkpoint / resume (the reference keeps the filter only in the node's memory, slam.cpp:427-430): the batch's arrays
+ * exactly as the engine holds them — Sigma packed symmetric, sizes from ekf_batch_checkpoint_size — plus
+ * landmark_init_flag [B], known_list [B][n] and the update counter.  A batch of the same shape restored with
+ * ekf_batch_import continues bit-identically. */
+int ekf_batch_checkpoint_size(ekf_batch* b, int64_t* sigma_doubles, int64_t* state_doubles);
+int ekf_batch_export(ekf_batch* b, double* sigma, double* state, int32_t* init_flag, uint8_t* known, uint64_t* updates);
+int ekf_batch_import(ekf_batch* b, const double* sigma, const double* state, const int32_t* init_flag,
+                     const uint8_t* known, uint64_t updates);
 /* error statistics against ground-truth poses truth[B][3] = {x, y, theta}:
  * out4 = {sum dx^2, sum dy^2, sum wrap(dtheta)^2, B} — the per-GPU partial that ranks all-reduce. */
 int ekf_batch_pose_error(ekf_batch* b, const double* truth, double* out4);

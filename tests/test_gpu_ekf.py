@@ -247,6 +247,39 @@ def test_batch_marker_list_equals_dense_arrays(gpu_pkg, n):
     assert np.array_equal(sparse.states(), before)
 
 
+def test_batch_checkpoint_resume_is_bit_identical(gpu_pkg, tmp_path):
+    """Checkpoint / resume: a restored batch continues exactly where the original would have."""
+    tg = gpu_pkg.tracegen
+    B, T, M = 64, 16, 8
+    tr = tg.simulate_known(tg.dense_world(20), B, T, seed=21)
+    tu = tg.simulate_unknown(tg.default_world(20), B, T, seed=22, m_max=M)
+    for mode in ("known", "unknown"):
+        a, b = gpu_pkg.EKFBatch(B, 20), gpu_pkg.EKFBatch(B, 20)
+
+        def step(bt, t):
+            if mode == "known":
+                bt.step_known(np.ascontiguousarray(tr["twists"][t]), np.ascontiguousarray(tr["xy"][t]),
+                              np.ascontiguousarray(tr["vis"][t]))
+            else:
+                bt.step_unknown(np.ascontiguousarray(tu["twists"][t]), np.ascontiguousarray(tu["meas"][t]),
+                                np.ascontiguousarray(tu["count"][t]), M)
+            bt.sync()
+
+        for t in range(T // 2):
+            step(a, t)
+        path = str(tmp_path / f"ck_{mode}.npz")
+        a.save_checkpoint(path)
+        b.load_checkpoint(path)
+        assert b.update_count == a.update_count
+        for t in range(T // 2, T):
+            step(a, t)
+            step(b, t)
+        assert np.array_equal(a.states(), b.states()) and np.array_equal(a.known, b.known)
+        assert np.array_equal(a.sigma(B - 1), b.sigma(B - 1)) and a.update_count == b.update_count
+    with pytest.raises(ValueError):
+        gpu_pkg.EKFBatch(B + 1, 20).restore(a.checkpoint())
+
+
 def test_batch_unknown_matches_oracle(gpu_pkg):
     tg = gpu_pkg.tracegen
     B, T, M = 40, 30, 10
