@@ -259,22 +259,28 @@ __device__ __forceinline__ void sym_warp_rank2(double* __restrict__ sig, const d
     __syncwarp();
 }
 
-// Mahalanobis distance from the 5 x 5 block of the staircase Sigma (ekf_slam.cpp:217-276; see maha_distance_rows).
-__device__ __forceinline__ double sym_maha_distance(const double* __restrict__ sig, int N, int i, double mx, double my,
-                                                    double zr, double zphi, double theta, double x, double y) {
+// Mahalanobis distance from the 5 x 5 block Sigma[idx, idx], idx = {0, 1, 2, 3+2i, 4+2i} (ekf_slam.cpp:217-276; see
+// maha_distance_rows).  The block is symmetric: 15 distinct entries, of which the robot's 3 x 3 corner `rob`
+// (00 01 02 11 12 22) is the same for every landmark and is fetched once per measurement by the caller.
+__device__ __forceinline__ double sym_maha_distance(const double* __restrict__ sig, int N, int i, const double* rob,
+                                                    double mx, double my, double zr, double zphi, double theta,
+                                                    double x, double y) {
     const Hj h = make_hj(mx, my, theta, x, y);
     const int i3 = 3 + 2 * i, i4 = i3 + 1;
-    const int id[5] = {0, 1, 2, i3, i4};
+    const int rb3 = stair_row_base(i3, N) - (i3 & ~15), rb4 = stair_row_base(i4, N) - (i4 & ~15);
+    const double c03 = sig[i3], c04 = sig[i4], c13 = sig[N + i3], c14 = sig[N + i4], c23 = sig[2 * N + i3],
+                 c24 = sig[2 * N + i4];
+    const double l33 = sig[rb3 + i3], l34 = sig[rb3 + i4], l44 = sig[rb4 + i4];
+    const double blk[5][5] = {{rob[0], rob[1], rob[2], c03, c04},
+                              {rob[1], rob[3], rob[4], c13, c14},
+                              {rob[2], rob[4], rob[5], c23, c24},
+                              {c03, c13, c23, l33, l34},
+                              {c04, c14, c24, l34, l44}};
     double wl0[5], wl1[5];
 #pragma unroll
     for (int l = 0; l < 5; ++l) {
-        const double s0 = sig[id[l]];
-        const double s1 = sig[N + id[l]];
-        const double s2 = sig[2 * N + id[l]];
-        const double s3 = sig[stair_at(i3, id[l], N)];
-        const double s4 = sig[stair_at(i4, id[l], N)];
-        wl0[l] = h_row0(h, s1, s2, s3, s4);
-        wl1[l] = h_row1(h, s0, s1, s2, s3, s4);
+        wl0[l] = h_row0(h, blk[1][l], blk[2][l], blk[3][l], blk[4][l]);
+        wl1[l] = h_row1(h, blk[0][l], blk[1][l], blk[2][l], blk[3][l], blk[4][l]);
     }
     const double p00 = h_row0(h, wl0[1], wl0[2], wl0[3], wl0[4]) + kR;
     const double p01 = h_row1(h, wl0[0], wl0[1], wl0[2], wl0[3], wl0[4]);
@@ -512,8 +518,9 @@ __global__ void __launch_bounds__(32, NL == 20 ? EKF_SYM_MINB : 1) ekf_fused_sym
             const double theta = st[0], x = st[1], y = st[2];  // live pose (:219-221)
             double best = INFINITY, second = INFINITY;
             int best_i = 0x7fffffff;
+            const double rob[6] = {sig[0], sig[1], sig[2], sig[N + 1], sig[N + 2], sig[2 * N + 2]};
             for (int i = lane; i < known_count; i += 32) {
-                double d = sym_maha_distance(sig, N, i, st[3 + 2 * i], st[4 + 2 * i], zr, zphi, theta, x, y);
+                double d = sym_maha_distance(sig, N, i, rob, st[3 + 2 * i], st[4 + 2 * i], zr, zphi, theta, x, y);
                 if (!(d == d)) d = INFINITY;  // NaN never wins
                 if (d < best) {
                     second = best;
