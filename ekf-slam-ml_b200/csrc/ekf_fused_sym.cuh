@@ -131,18 +131,17 @@ __device__ __forceinline__ void sym_warp_gain(const double* __restrict__ sig, do
                 s3 = apply_pair(s3, t3 ? kc : ka[3], t3 ? wa3 : wc);
                 s4 = apply_pair(s4, t4 ? kc : ka[4], t4 ? wa4 : wc);
             }
-            wreg[sl] = make_double2(h_row0(h, s1, s2, s3, s4), h_row1(h, s0, s1, s2, s3, s4));
+            h_rows(h, s0, s1, s2, s3, s4, wreg[sl].x, wreg[sl].y);
             Wout[c] = wreg[sl];
         }
     }
     __syncwarp();
     // S = (Hj Sigma) Hj^T + R from W at the five columns; closed-form inverse
     const double2 w0 = Wout[0], w1 = Wout[1], w2 = Wout[2], w3 = Wout[i3], w4 = Wout[i4];
-    const double s00 = h_row0(h, w1.x, w2.x, w3.x, w4.x) + kR;
-    const double s01 = h_row1(h, w0.x, w1.x, w2.x, w3.x, w4.x);
-    const double s10 = h_row0(h, w1.y, w2.y, w3.y, w4.y);
-    const double s11 = h_row1(h, w0.y, w1.y, w2.y, w3.y, w4.y) + kR;
-    const Sym2 si = inv2x2(s00, s01, s10, s11);
+    double s00, s01, s10, s11;
+    h_rows(h, w0.x, w1.x, w2.x, w3.x, w4.x, s00, s01);
+    h_rows(h, w0.y, w1.y, w2.y, w3.y, w4.y, s10, s11);
+    const Sym2 si = inv2x2(s00 + kR, s01, s10, s11 + kR);
     // K = W^T S^-1 folded with nu: state += K nu
 #pragma unroll
     for (int sl = 0; sl < NS; ++sl) {
@@ -278,15 +277,11 @@ __device__ __forceinline__ double sym_maha_distance(const double* __restrict__ s
                               {c04, c14, c24, l34, l44}};
     double wl0[5], wl1[5];
 #pragma unroll
-    for (int l = 0; l < 5; ++l) {
-        wl0[l] = h_row0(h, blk[1][l], blk[2][l], blk[3][l], blk[4][l]);
-        wl1[l] = h_row1(h, blk[0][l], blk[1][l], blk[2][l], blk[3][l], blk[4][l]);
-    }
-    const double p00 = h_row0(h, wl0[1], wl0[2], wl0[3], wl0[4]) + kR;
-    const double p01 = h_row1(h, wl0[0], wl0[1], wl0[2], wl0[3], wl0[4]);
-    const double p10 = h_row0(h, wl1[1], wl1[2], wl1[3], wl1[4]);
-    const double p11 = h_row1(h, wl1[0], wl1[1], wl1[2], wl1[3], wl1[4]) + kR;
-    const Sym2 pi = inv2x2(p00, p01, p10, p11);
+    for (int l = 0; l < 5; ++l) h_rows(h, blk[0][l], blk[1][l], blk[2][l], blk[3][l], blk[4][l], wl0[l], wl1[l]);
+    double p00, p01, p10, p11;
+    h_rows(h, wl0[0], wl0[1], wl0[2], wl0[3], wl0[4], p00, p01);
+    h_rows(h, wl1[0], wl1[1], wl1[2], wl1[3], wl1[4], p10, p11);
+    const Sym2 pi = inv2x2(p00 + kR, p01, p10, p11 + kR);
     const double v0 = __dsub_rn(zr, h.zr), v1 = __dsub_rn(zphi, h.zphi);
     const double t0 = __dadd_rn(__dmul_rn(v0, pi.i00), __dmul_rn(v1, pi.i10));
     const double t1 = __dadd_rn(__dmul_rn(v0, pi.i01), __dmul_rn(v1, pi.i11));
