@@ -82,3 +82,14 @@ def test_sim_to_filter_stays_on_device(gpu_pkg):
     np.testing.assert_allclose(bt.states(), bh.states(), rtol=0, atol=1e-7)
     err = bt.pose_error(sim.download()["truth"])
     assert np.all(np.sqrt(err[:3] / B) < 0.1)
+
+
+def test_accuracy_report(gpu_pkg):
+    """the README's Actual / Odom / Slam comparison over a batch of seeds."""
+    r = gpu_pkg.report.run(gpu_pkg, robots=512, steps=40, seed=4)
+    e = r["rmse_xytheta"]
+    assert r["updates"] > 512 * 40 and np.isfinite(r["landmark_rmse"]) and r["landmark_rmse"] < 0.05
+    assert e["slam"][0] < 0.05 and e["slam"][1] < 0.05
+    assert e["slam"][1] < e["prediction_only"][1]            # the filter beats dead reckoning on the 10 Hz twist
+    assert e["wheel_odometry"][0] < 1e-9                     # the 100 Hz odometer sees the truth's own increments
+    assert "Slam" in gpu_pkg.report.markdown(r)
