@@ -178,34 +178,30 @@ def large_map_leg(pkg, device, n_lm, timed_updates, peak_gbs, want_cpu):
     steps = 64
     tr = tg.simulate_known(w, 1, steps, seed=99)
     f = pkg.EKF_SLAM(n_lm, device=device)
+    if os.environ.get("EKF_BENCH_MAX_PENDING"):  # tuning aid
+        f.set_max_pending(int(os.environ["EKF_BENCH_MAX_PENDING"]))
     N = 3 + 2 * n_lm
-    # first call: initialise every landmark (ekf_slam.cpp:113-128), then a few warm-up corrections
+    # first call: initialise every landmark (ekf_slam.cpp:113-128), then a few warm-up steps, then ONE timed region
+    # over whole SLAM steps until `timed_updates` corrections are done.  Factors stay pending across steps, so the
+    # region ends with the flush that timer_stop() triggers (inside the timed region).
     t = 0
-    done = 0
-    per_update_ms = []
-    l0 = None
-    n_sweeps, sweep_ms_total = 0, 0.0
-    while t < steps:
-        nvis = int(tr["vis"][t, 0].sum())
-        timed = t >= 3
-        if timed and l0 is None:
-            l0 = f.launch_count
-        if timed and nvis:
-            f.sync()
-            f.timer_start()
+    while t < 3:
         f.prediction(tuple(tr["twists"][t, 0]))
         f.measurement(tr["xy"][t, 0], tr["vis"][t, 0])
-        if timed and nvis:
-            ms = f.timer_stop()
-            per_update_ms.append(ms / nvis)
-            done += nvis
-            n_sweeps += -(-nvis // 8)  # up to 8 corrections are applied per pass over Sigma (kMaxPending)
-            sweep_ms_total += ms
         t += 1
-        if done >= timed_updates:
-            break
-    launches = f.launch_count - (l0 or 0)
-    ms_upd = float(np.mean(per_update_ms))
+    f.sync()
+    l0, s0 = f.launch_count, f.sweep_count
+    done = 0
+    f.timer_start()
+    while t < steps and done < timed_updates:
+        f.prediction(tuple(tr["twists"][t, 0]))
+        f.measurement(tr["xy"][t, 0], tr["vis"][t, 0])
+        done += int(tr["vis"][t, 0].sum())
+        t += 1
+    sweep_ms_total = f.timer_stop()
+    launches = f.launch_count - l0
+    n_sweeps = f.sweep_count - s0
+    ms_upd = sweep_ms_total / max(done, 1)
     alg_bytes = 16.0 * N * N
     out = {
         "workload": f"cfg4: single map, n={n_lm} landmarks (N={N}, Sigma {8.0 * N * N / 1e9:.3f} GB), known association, "
@@ -221,7 +217,7 @@ def large_map_leg(pkg, device, n_lm, timed_updates, peak_gbs, want_cpu):
                      "updates_per_sweep": done / max(n_sweeps, 1),
                      "per_update_achieved": alg_bytes / (ms_upd * 1e-3) / 1e9,
                      "per_update_frac": alg_bytes / (ms_upd * 1e-3) / 1e9 / peak_gbs,
-                     "note": "one launch moves Sigma once (16 N^2 B) and applies up to 8 pending corrections; per_update_* "
+                     "note": "one launch moves Sigma once (16 N^2 B) and applies up to 12 pending corrections; per_update_* "
                              "is SURVEY.md's 16 N^2-per-correction convention and exceeds 1 for that reason"},
     }
     if want_cpu:
@@ -254,24 +250,23 @@ def sharded_map_leg(pkg, dist, local, n_lm, timed_updates, peak_gbs):
     tr = tg.simulate_known(w, 1, steps, seed=77)
     f = ShardedEKF.from_process_group(n_lm, dist, local)
     N = 3 + 2 * n_lm
-    done, t, total_ms, n_sweeps = 0, 0, 0.0, 0
-    l0 = None
-    while t < steps and done < timed_updates:
-        nvis = int(tr["vis"][t, 0].sum())
-        timed = t >= 2
-        if timed and l0 is None:
-            l0 = f.launch_count
-        if timed and nvis:
-            f.sync()
-            dist.barrier()
-            f.timer_start()
+    t = 0
+    while t < 2:  # init-only call + one warm-up step
         f.prediction(tuple(tr["twists"][t, 0]))
         f.measurement(tr["xy"][t, 0], tr["vis"][t, 0])
-        if timed and nvis:
-            total_ms += pkg.sharding.allreduce_max(f.timer_stop(), dist, "cuda")
-            done += nvis
-            n_sweeps += -(-nvis // 8)
         t += 1
+    f.sync()
+    dist.barrier()
+    l0, s0 = f.launch_count, f.sweep_count
+    done = 0
+    f.timer_start()
+    while t < steps and done < timed_updates:  # one timed region; factors stay pending across steps
+        f.prediction(tuple(tr["twists"][t, 0]))
+        f.measurement(tr["xy"][t, 0], tr["vis"][t, 0])
+        done += int(tr["vis"][t, 0].sum())
+        t += 1
+    total_ms = pkg.sharding.allreduce_max(f.timer_stop(), dist, "cuda")  # timer_stop settles the pending factors first
+    n_sweeps = f.sweep_count - s0
     ms_upd = total_ms / max(done, 1)
     rows = f.rows(0)
     per_gpu_bytes = 16.0 * N * N / world
@@ -279,7 +274,7 @@ def sharded_map_leg(pkg, dist, local, n_lm, timed_updates, peak_gbs):
         "workload": f"cfg5: single map, n={n_lm} landmarks (N={N}, Sigma {8.0 * N * N / 1e9:.1f} GB) row-block-sharded over "
                     f"{world} GPUs; per correction: one NCCL all-reduce of W (2N fp64), K = W^T S^-1 formed on every rank, sweep of own rows",
         "value": 1e3 / ms_upd, "unit": UNIT, "updates_timed": done, "ms_per_update": ms_upd,
-        "gpu_launches_rank0": int(f.launch_count - (l0 or 0)), "rows_rank0": list(rows),
+        "gpu_launches_rank0": int(f.launch_count - l0), "rows_rank0": list(rows),
         "roofline": {"bound": "hbm", "kernel": "k_large_sweep_p<P> on each rank's rows (time per sweep = whole step incl. "
                                                 "prediction, gains and the NCCL exchanges)",
                      "achieved": per_gpu_bytes * n_sweeps / (total_ms * 1e-3) / 1e9, "peak": peak_gbs, "unit": "GB/s per GPU",

@@ -53,6 +53,8 @@ SIGNATURES = {
     "ekf_device_pointers": (ctypes.c_int, [ctypes.c_void_p, c_void_pp, c_i64_p, c_void_pp]),
     "ekf_stream": (ctypes.c_void_p, [ctypes.c_void_p]),
     "ekf_launch_count": (ctypes.c_int, [ctypes.c_void_p, c_u64_p]),
+    "ekf_sweep_count": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_uint64)]),
+    "ekf_set_carry_pending": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     "ekf_set_max_pending": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     "ekf_batch_create": (ctypes.c_int, [ctypes.c_int64, ctypes.c_int, ctypes.c_int, c_void_pp]),
     "ekf_batch_destroy": (ctypes.c_int, [ctypes.c_void_p]),
@@ -140,6 +142,8 @@ SIGNATURES_SHARDED = {
     "ekf_sharded_rows": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, c_i64_p, c_i64_p]),
     "ekf_sharded_get_sigma_rows": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, c_double_p, ctypes.c_int64]),
     "ekf_sharded_update_count": (ctypes.c_int, [ctypes.c_void_p, c_u64_p]),
+    "ekf_sharded_sweep_count": (ctypes.c_int, [ctypes.c_void_p, c_u64_p]),
+    "ekf_sharded_set_carry_pending": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     "ekf_sharded_launch_count": (ctypes.c_int, [ctypes.c_void_p, c_u64_p]),
     "ekf_sharded_sync": (ctypes.c_int, [ctypes.c_void_p]),
     "ekf_sharded_timer_start": (ctypes.c_int, [ctypes.c_void_p]),

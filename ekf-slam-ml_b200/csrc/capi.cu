@@ -223,6 +223,8 @@ struct ekf_filter {
     double* d_state_alt = nullptr;  // ping-pong partner of d_state (the gain kernel never writes what it reads)
     int pending = 0;                // corrections computed but not yet applied to Sigma
     int max_pending = kMaxPending;  // flush threshold (1 = the reference's one sweep per correction)
+    int carry_pending = 1;          // factors may stay pending across prediction() / measurement() calls
+    uint64_t sweeps = 0;            // passes over Sigma so far (streamed engine)
     double* d_motion = nullptr;
     double* d_pose0 = nullptr;
     UpdateCmd* d_cmd = nullptr;
@@ -356,6 +358,7 @@ int stream_flush(ekf_filter* h, int n_counted, const UpdateCmd* cmd) {
     CU(launch_sweep(h->pending, h->d_sigma, h->ld, h->N, h->d_K2, h->d_W2, 0, h->d_nupd, n_counted, cmd, h->sm_count,
                       h->stream));
     h->launches += 1;
+    h->sweeps += 1;
     h->pending = 0;
     return EKF_OK;
 }
@@ -372,6 +375,13 @@ int stream_correct(ekf_filter* h, const double* pose_src, const UpdateCmd* cmd, 
     h->pending += 1;
     if (h->pending >= h->max_pending) return stream_flush(h, cmd ? 0 : h->pending, nullptr);
     return EKF_OK;
+}
+
+// Verbs that look at Sigma or at the update counter first bring Sigma up to date (factors may stay pending across
+// prediction() and measurement() calls).
+int stream_settle(ekf_filter* h) {
+    if (h->engine == EKF_ENGINE_FUSED || h->pending == 0) return EKF_OK;
+    return stream_flush(h, h->pending, nullptr);
 }
 
 }  // namespace
@@ -498,6 +508,8 @@ int ekf_clone(ekf_filter* src, ekf_filter** out) {
     if (rc) return rc;
     ekf_filter* h = *out;
     DeviceGuard g(src->device);
+    rc = stream_settle(src);
+    if (rc) return rc;
     CU(cudaStreamSynchronize(src->stream));
     CU(cudaMemcpy(h->d_sigma, src->d_sigma, sizeof(double) * (size_t)src->sig_elems, cudaMemcpyDeviceToDevice));
     CU(cudaMemcpy(h->d_state, src->d_state, sizeof(double) * src->st_stride, cudaMemcpyDeviceToDevice));
@@ -530,9 +542,17 @@ int ekf_predict(ekf_filter* h, double dtheta, double dx) {
         h->launches += 1;
         return rc;
     }
+    if (h->pending > 0 && !h->carry_pending) {
+        int rc = stream_flush(h, h->pending, nullptr);
+        if (rc) return rc;
+    }
     k_large_motion<<<1, 32, 0, h->stream>>>(h->d_state, h->d_sigma, h->ld, dtheta, dx, h->d_motion);
     k_large_predict_strips<<<(h->N - 3 + 255) / 256, 256, 0, h->stream>>>(h->d_sigma, h->ld, h->N, h->d_motion);
     h->launches += 2;
+    if (h->pending > 0) {  // factors carried across the prediction (ekf_large_delayed.cuh)
+        k_large_predict_factors<<<1, 32, 0, h->stream>>>(h->d_K2, h->d_W2, h->ld, h->pending, h->d_motion);
+        h->launches += 1;
+    }
     CU(cudaGetLastError());
     return EKF_OK;
 }
@@ -576,13 +596,18 @@ int ekf_measurement(ekf_filter* h, const double* xy, const uint8_t* visible) {
         int rc = stream_correct(h, h->d_pose0, nullptr, i, xy[2 * i], xy[2 * i + 1]);
         if (rc) return rc;
     }
-    return stream_flush(h, h->pending, nullptr);
+    // with carry_pending the factors wait for more corrections (up to max_pending) before Sigma is swept
+    return h->carry_pending ? EKF_OK : stream_flush(h, h->pending, nullptr);
 }
 
 int ekf_data_association(ekf_filter* h, const double* xy, int m, uint8_t* known, int32_t* assoc_out,
                          double* dmin_out, double* second_out, uint8_t* created_out) {
     if (!h || !known || m < 0 || (m > 0 && !xy)) return fail(EKF_ERR_INVALID, "invalid argument");
     DeviceGuard g(h->device);
+    {
+        int rc_ = stream_settle(h);
+        if (rc_) return rc_;
+    }
     const int n = h->n;
     if (m == 0) return EKF_OK;
     int rc = ensure_m_cap(h, m);
@@ -654,6 +679,10 @@ int ekf_data_association(ekf_filter* h, const double* xy, int m, uint8_t* known,
 int ekf_maha(ekf_filter* h, double mx, double my, int landmark, double* d_out) {
     if (!h || !d_out || landmark < 0 || landmark >= h->n) return fail(EKF_ERR_INVALID, "invalid argument");
     DeviceGuard g(h->device);
+    {
+        int rc_ = stream_settle(h);
+        if (rc_) return rc_;
+    }
     k_maha_one<<<1, 1, 0, h->stream>>>(h->d_sigma, h->ld, h->d_state, landmark, mx, my, h->d_scalar);
     h->launches += 1;
     CU(cudaGetLastError());
@@ -693,6 +722,10 @@ int ekf_get_landmarks(ekf_filter* h, double* out) {
 int ekf_get_sigma(ekf_filter* h, double* out, int64_t ld) {
     if (!h || !out || ld < h->N) return fail(EKF_ERR_INVALID, "invalid argument");
     DeviceGuard g(h->device);
+    {
+        int rc_ = stream_settle(h);
+        if (rc_) return rc_;
+    }
     CU(cudaMemcpy2DAsync(out, sizeof(double) * ld, h->d_sigma, sizeof(double) * h->ld, sizeof(double) * h->N, h->N,
                          cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
@@ -701,6 +734,10 @@ int ekf_get_sigma(ekf_filter* h, double* out, int64_t ld) {
 int ekf_set_sigma(ekf_filter* h, const double* in, int64_t ld) {
     if (!h || !in || ld < h->N) return fail(EKF_ERR_INVALID, "invalid argument");
     DeviceGuard g(h->device);
+    {
+        int rc_ = stream_settle(h);
+        if (rc_) return rc_;
+    }
     CU(cudaMemcpy2DAsync(h->d_sigma, sizeof(double) * h->ld, in, sizeof(double) * ld, sizeof(double) * h->N, h->N,
                          cudaMemcpyHostToDevice, h->stream));
     CU(cudaStreamSynchronize(h->stream));
@@ -727,6 +764,10 @@ int ekf_set_init_flag(ekf_filter* h, int v) {
 int ekf_update_count(ekf_filter* h, uint64_t* out) {
     if (!h || !out) return fail(EKF_ERR_INVALID, "null argument");
     DeviceGuard g(h->device);
+    {
+        int rc_ = stream_settle(h);
+        if (rc_) return rc_;
+    }
     unsigned long long v = 0;
     CU(cudaMemcpyAsync(&v, h->d_nupd, sizeof(v), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
@@ -736,11 +777,20 @@ int ekf_update_count(ekf_filter* h, uint64_t* out) {
 int ekf_sync(ekf_filter* h) {
     if (!h) return fail(EKF_ERR_INVALID, "null handle");
     DeviceGuard g(h->device);
+    {
+        int rc_ = stream_settle(h);
+        if (rc_) return rc_;
+    }
     CU(cudaStreamSynchronize(h->stream));
     return EKF_OK;
 }
 int ekf_device_pointers(ekf_filter* h, void** sigma, int64_t* ld, void** state) {
     if (!h) return fail(EKF_ERR_INVALID, "null handle");
+    {
+        DeviceGuard g(h->device);
+        int rc_ = stream_settle(h);
+        if (rc_) return rc_;
+    }
     if (sigma) *sigma = h->d_sigma;
     if (ld) *ld = h->ld;
     if (state) *state = h->d_state;
@@ -751,6 +801,28 @@ int ekf_device_pointers(ekf_filter* h, void** sigma, int64_t* ld, void** state) 
 int ekf_set_max_pending(ekf_filter* h, int max_pending) {
     if (!h || max_pending < 1 || max_pending > kMaxPending) return fail(EKF_ERR_INVALID, "max_pending must be 1..%d", kMaxPending);
     h->max_pending = max_pending;
+    if (h->pending >= max_pending) {
+        DeviceGuard g(h->device);
+        return stream_settle(h);
+    }
+    return EKF_OK;
+}
+// 1 (default): factor pairs may stay pending across prediction() and measurement() calls, so that every sweep of the
+// streamed engine carries max_pending corrections; 0: Sigma is brought up to date at the end of every measurement()
+// (then the delayed application is bit-identical to one sweep per correction).  Either way every verb that reads
+// Sigma settles it first.
+int ekf_set_carry_pending(ekf_filter* h, int carry) {
+    if (!h) return fail(EKF_ERR_INVALID, "null handle");
+    h->carry_pending = carry ? 1 : 0;
+    if (!h->carry_pending) {
+        DeviceGuard g(h->device);
+        return stream_settle(h);
+    }
+    return EKF_OK;
+}
+int ekf_sweep_count(ekf_filter* h, uint64_t* out) {
+    if (!h || !out) return fail(EKF_ERR_INVALID, "null argument");
+    *out = h->sweeps;
     return EKF_OK;
 }
 int ekf_launch_count(ekf_filter* h, uint64_t* out) {
@@ -772,6 +844,10 @@ int ekf_timer_start(ekf_filter* h) {
 int ekf_timer_stop(ekf_filter* h, float* ms_out) {
     if (!h || !ms_out || !h->t0) return fail(EKF_ERR_INVALID, "timer not started");
     DeviceGuard g(h->device);
+    {
+        int rc_ = stream_settle(h);
+        if (rc_) return rc_;
+    }
     CU(cudaEventRecord(h->t1, h->stream));
     CU(cudaEventSynchronize(h->t1));
     CU(cudaEventElapsedTime(ms_out, h->t0, h->t1));

@@ -11,7 +11,12 @@
 
 namespace ekf {
 
-constexpr int kMaxPending = 8;
+// 12: measured optimum of the TMA sweep on B200 at N = 16,387 (per correction 0.101 ms at 8, 0.086 at 10, 0.077 at 12,
+// 0.084 at 14, 0.101 at 16: beyond 12 the consumers' W pairs no longer fit the register file)
+#ifndef EKF_MAX_PENDING
+#define EKF_MAX_PENDING 12
+#endif
+constexpr int kMaxPending = EKF_MAX_PENDING;
 
 struct GainSharedP {
     Hj h;
@@ -121,6 +126,24 @@ __global__ void __launch_bounds__(256)
     double ns = st_k + fma(k1, g.nu1, k0 * g.nu0);
     if (k == 0) ns = normalize_angle(ns);  // ekf_slam.cpp:187
     state_out[k] = ns;
+}
+
+// prediction() with factors pending: Sigma' = A (Sigma_0 - sum_j K_j W_j) A^T + Q = [A Sigma_0 A^T + Q] - sum_j (A K_j)(W_j A^T)
+// with A = I + a1 e1 e0^T + a2 e2 e0^T (ekf_slam.cpp:89-102).  The bracket is the usual strip update of the stored
+// Sigma_0; the factors take K_j[1] += a1 K_j[0], K_j[2] += a2 K_j[0] and W_j[:,1] += a1 W_j[:,0], W_j[:,2] += a2 W_j[:,0]:
+// O(1) per factor, so the sweep does not have to run before every prediction and a group can span SLAM steps.
+__global__ void k_large_predict_factors(double2* __restrict__ Kp, double2* __restrict__ Wp, long long ld, int pending,
+                                        const double* __restrict__ motion) {
+    const int j = threadIdx.x;
+    if (j >= pending) return;
+    const double a1 = motion[0], a2 = motion[1];
+    double2* K = Kp + (long long)j * ld;
+    double2* W = Wp + (long long)j * ld;
+    const double2 k0 = K[0], w0 = W[0];
+    K[1] = make_double2(fma(a1, k0.x, K[1].x), fma(a1, k0.y, K[1].y));
+    K[2] = make_double2(fma(a2, k0.x, K[2].x), fma(a2, k0.y, K[2].y));
+    W[1] = make_double2(fma(a1, w0.x, W[1].x), fma(a1, w0.y, W[1].y));
+    W[2] = make_double2(fma(a2, w0.x, W[2].x), fma(a2, w0.y, W[2].y));
 }
 
 // Sigma[r][c] <- Sigma[r][c] - sum_{j<P} K_j[r] W_j[c], one pass over Sigma.  COLS columns per thread (4 -> 256-bit

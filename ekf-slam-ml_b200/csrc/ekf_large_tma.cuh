@@ -20,6 +20,10 @@
 #include "bulk_copy.cuh"
 #include "ekf_large_delayed.cuh"
 
+#ifndef EKF_TMA_NARROW_FROM
+#define EKF_TMA_NARROW_FROM 5  // pending-factor count from which the consumers use the 2-column mapping
+#endif
+
 namespace ekf {
 
 constexpr int kTmaCols = 512;
@@ -37,7 +41,9 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 }
 __device__ __forceinline__ void bulk_wait_read_1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 
-template <int P>
+// NARROW = false: a consumer thread owns 4 columns x 4 rows of a stage (16 P registers of W pairs);
+// NARROW = true : 2 columns x all 8 rows (8 P registers), which keeps P = 7, 8 out of local memory.
+template <int P, bool NARROW = (P >= EKF_TMA_NARROW_FROM)>
 __global__ void __launch_bounds__(kTmaThreads, 1)
     k_large_sweep_tma(double* __restrict__ sig, long long ld, int n_rows, const double2* __restrict__ Kp,
                       const double2* __restrict__ Wp, long long row0, unsigned long long* __restrict__ n_updates,
@@ -99,59 +105,103 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
         } else if (warp <= kTmaConsumerWarps) {
             // ---------------------------------------------------------------- consumers
             const int w = warp - 1;
-            const int t = 32 * (w & 3) + lane;
-            const int ca = 2 * t, cb = kTmaCols / 2 + 2 * t;
-            const bool has_a = ca < width, has_b = cb < width;
-            const int kr0 = 4 * (w >> 2);  // first row of this warp's half of the stage
-            double2 wv[P][4];
-#pragma unroll
-            for (int j = 0; j < P; ++j) {
-                const double2* wj = Wp + (long long)j * ld + c0;
-                wv[j][0] = has_a ? wj[ca] : make_double2(0.0, 0.0);
-                wv[j][1] = has_a ? wj[ca + 1] : make_double2(0.0, 0.0);
-                wv[j][2] = has_b ? wj[cb] : make_double2(0.0, 0.0);
-                wv[j][3] = has_b ? wj[cb + 1] : make_double2(0.0, 0.0);
-            }
-            for (int g = 0; g < groups; ++g) {
-                const int r = r_begin + g * kStageRows;
-                const int nr = r_end - r < kStageRows ? r_end - r : kStageRows;
-                mbar_wait(full + stage, phase);
-                double* tile = tiles + (size_t)stage * kStageRows * kTmaCols;
-                const double2* kst = ksm + (size_t)stage * kMaxPending * kStageRows;
-                double2 va[4], vb[4];
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    va[k] = make_double2(0.0, 0.0);
-                    vb[k] = make_double2(0.0, 0.0);
-                    if (kr0 + k < nr) {
-                        if (has_a) va[k] = *reinterpret_cast<const double2*>(tile + (kr0 + k) * kTmaCols + ca);
-                        if (has_b) vb[k] = *reinterpret_cast<const double2*>(tile + (kr0 + k) * kTmaCols + cb);
-                    }
-                }
+            if constexpr (!NARROW) {
+                const int t = 32 * (w & 3) + lane;
+                const int ca = 2 * t, cb = kTmaCols / 2 + 2 * t;
+                const bool has_a = ca < width, has_b = cb < width;
+                const int kr0 = 4 * (w >> 2);  // first row of this warp's half of the stage
+                double2 wv[P][4];
 #pragma unroll
                 for (int j = 0; j < P; ++j) {
+                    const double2* wj = Wp + (long long)j * ld + c0;
+                    wv[j][0] = has_a ? wj[ca] : make_double2(0.0, 0.0);
+                    wv[j][1] = has_a ? wj[ca + 1] : make_double2(0.0, 0.0);
+                    wv[j][2] = has_b ? wj[cb] : make_double2(0.0, 0.0);
+                    wv[j][3] = has_b ? wj[cb + 1] : make_double2(0.0, 0.0);
+                }
+                for (int g = 0; g < groups; ++g) {
+                    const int r = r_begin + g * kStageRows;
+                    const int nr = r_end - r < kStageRows ? r_end - r : kStageRows;
+                    mbar_wait(full + stage, phase);
+                    double* tile = tiles + (size_t)stage * kStageRows * kTmaCols;
+                    const double2* kst = ksm + (size_t)stage * kMaxPending * kStageRows;
+                    double2 va[4], vb[4];
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
-                        const double2 kk = kst[j * kStageRows + kr0 + k];
-                        va[k].x = apply_factor(va[k].x, kk, wv[j][0]);
-                        va[k].y = apply_factor(va[k].y, kk, wv[j][1]);
-                        vb[k].x = apply_factor(vb[k].x, kk, wv[j][2]);
-                        vb[k].y = apply_factor(vb[k].y, kk, wv[j][3]);
+                        va[k] = make_double2(0.0, 0.0);
+                        vb[k] = make_double2(0.0, 0.0);
+                        if (kr0 + k < nr) {
+                            if (has_a) va[k] = *reinterpret_cast<const double2*>(tile + (kr0 + k) * kTmaCols + ca);
+                            if (has_b) vb[k] = *reinterpret_cast<const double2*>(tile + (kr0 + k) * kTmaCols + cb);
+                        }
                     }
-                }
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    if (kr0 + k < nr) {
-                        if (has_a) *reinterpret_cast<double2*>(tile + (kr0 + k) * kTmaCols + ca) = va[k];
-                        if (has_b) *reinterpret_cast<double2*>(tile + (kr0 + k) * kTmaCols + cb) = vb[k];
+                    for (int j = 0; j < P; ++j) {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const double2 kk = kst[j * kStageRows + kr0 + k];
+                            va[k].x = apply_factor(va[k].x, kk, wv[j][0]);
+                            va[k].y = apply_factor(va[k].y, kk, wv[j][1]);
+                            vb[k].x = apply_factor(vb[k].x, kk, wv[j][2]);
+                            vb[k].y = apply_factor(vb[k].y, kk, wv[j][3]);
+                        }
+                    }
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        if (kr0 + k < nr) {
+                            if (has_a) *reinterpret_cast<double2*>(tile + (kr0 + k) * kTmaCols + ca) = va[k];
+                            if (has_b) *reinterpret_cast<double2*>(tile + (kr0 + k) * kTmaCols + cb) = vb[k];
+                        }
+                    }
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(done + stage);
+                    if (++stage == kStages) {
+                        stage = 0;
+                        phase ^= 1u;
                     }
                 }
-                fence_proxy_async_smem();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(done + stage);
-                if (++stage == kStages) {
-                    stage = 0;
-                    phase ^= 1u;
+            } else {
+                const int ca = 2 * (32 * w + lane);  // 256 threads x 2 columns = the 512-column tile
+                const bool has = ca < width;
+                double2 wv[P][2];
+#pragma unroll
+                for (int j = 0; j < P; ++j) {
+                    const double2* wj = Wp + (long long)j * ld + c0;
+                    wv[j][0] = has ? wj[ca] : make_double2(0.0, 0.0);
+                    wv[j][1] = has ? wj[ca + 1] : make_double2(0.0, 0.0);
+                }
+                for (int g = 0; g < groups; ++g) {
+                    const int r = r_begin + g * kStageRows;
+                    const int nr = r_end - r < kStageRows ? r_end - r : kStageRows;
+                    mbar_wait(full + stage, phase);
+                    double* tile = tiles + (size_t)stage * kStageRows * kTmaCols;
+                    const double2* kst = ksm + (size_t)stage * kMaxPending * kStageRows;
+                    double2 v[kStageRows];
+#pragma unroll
+                    for (int k = 0; k < kStageRows; ++k) {
+                        v[k] = make_double2(0.0, 0.0);
+                        if (k < nr && has) v[k] = *reinterpret_cast<const double2*>(tile + k * kTmaCols + ca);
+                    }
+#pragma unroll
+                    for (int j = 0; j < P; ++j) {
+#pragma unroll
+                        for (int k = 0; k < kStageRows; ++k) {
+                            const double2 kk = kst[j * kStageRows + k];
+                            v[k].x = apply_factor(v[k].x, kk, wv[j][0]);
+                            v[k].y = apply_factor(v[k].y, kk, wv[j][1]);
+                        }
+                    }
+#pragma unroll
+                    for (int k = 0; k < kStageRows; ++k)
+                        if (k < nr && has) *reinterpret_cast<double2*>(tile + k * kTmaCols + ca) = v[k];
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(done + stage);
+                    if (++stage == kStages) {
+                        stage = 0;
+                        phase ^= 1u;
+                    }
                 }
             }
         } else {
@@ -207,6 +257,18 @@ inline cudaError_t launch_sweep(int pending, double* sig, long long ld, int n_ro
         EKF_TMA_CASE(6)
         EKF_TMA_CASE(7)
         EKF_TMA_CASE(8)
+#if EKF_MAX_PENDING > 8
+        EKF_TMA_CASE(9)
+        EKF_TMA_CASE(10)
+        EKF_TMA_CASE(11)
+        EKF_TMA_CASE(12)
+#endif
+#if EKF_MAX_PENDING > 12
+        EKF_TMA_CASE(13)
+        EKF_TMA_CASE(14)
+        EKF_TMA_CASE(15)
+        EKF_TMA_CASE(16)
+#endif
         default:
             return cudaErrorInvalidValue;
     }

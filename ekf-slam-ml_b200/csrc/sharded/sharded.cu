@@ -336,6 +336,8 @@ struct ekf_sharded {
     cudaStream_t stream = nullptr;
     int init_flag_host = 0;
     int pending = 0;  // corrections whose factors are not yet applied to Sigma
+    int carry_pending = 1;  // factors may stay pending across prediction() / measurement() calls
+    uint64_t sweeps = 0;    // passes over Sigma so far
     int m_cap = 0;
     const double2** d_srcs = nullptr;  // local mode: device array of Wpart pointers
     uint64_t launches = 0;
@@ -498,8 +500,12 @@ int flush(ekf_sharded* h, int n_counted, bool use_cmd) {
         }
     }
     h->pending = 0;
+    h->sweeps += 1;
     return 0;
 }
+
+// verbs that look at Sigma or at the update counter first bring Sigma up to date
+int settle(ekf_sharded* h) { return h->pending ? flush(h, h->pending, false) : 0; }
 
 // one landmark correction across all shards: fills factor slot `pending`; Sigma is swept later (flush)
 int correct(ekf_sharded* h, bool use_cmd, bool stale_pose, int lm, double sx, double sy) {
@@ -678,6 +684,10 @@ int ekf_sharded_create_local(int n, int world, int device, ekf_sharded** out) {
 int ekf_sharded_predict(ekf_sharded* h, double dtheta, double dx) {
     if (!h) return fail(-1, "null handle");
     Dev g(h->device);
+    if (!h->carry_pending) {
+        int rc = settle(h);
+        if (rc) return rc;
+    }
     for (auto& s : h->sh) {
         k_sh_motion<<<1, 32, 0, h->stream>>>(s.state, s.rank == 0 ? s.sig : nullptr, h->ld, dtheta, dx, s.motion);
         h->launches++;
@@ -689,6 +699,10 @@ int ekf_sharded_predict(ekf_sharded* h, double dtheta, double dx) {
         }
         if (s.rows > lr_begin) {
             k_sh_predict_cols<<<(s.rows - lr_begin + 255) / 256, 256, 0, h->stream>>>(s.sig, h->ld, lr_begin, s.rows, s.motion);
+            h->launches++;
+        }
+        if (h->pending > 0) {  // factors carried across the prediction: A K_j, W_j A^T (ekf_large_delayed.cuh)
+            k_large_predict_factors<<<1, 32, 0, h->stream>>>(s.K2, s.W2, h->ld, h->pending, s.motion);
             h->launches++;
         }
     }
@@ -718,7 +732,7 @@ int ekf_sharded_measurement(ekf_sharded* h, const double* xy, const uint8_t* vis
         int rc = correct(h, false, true, i, xy[2 * i], xy[2 * i + 1]);
         if (rc) return rc;
     }
-    return flush(h, h->pending, false);
+    return h->carry_pending ? 0 : flush(h, h->pending, false);
 }
 
 int ekf_sharded_data_association(ekf_sharded* h, const double* xy, int m, uint8_t* known, int32_t* assoc_out,
@@ -726,6 +740,10 @@ int ekf_sharded_data_association(ekf_sharded* h, const double* xy, int m, uint8_
     if (!h || !known || m < 0 || (m > 0 && !xy)) return fail(-1, "invalid argument");
     if (m == 0) return 0;
     Dev g(h->device);
+    {
+        int rc_ = settle(h);
+        if (rc_) return rc_;
+    }
     const int n = h->n;
     int rc = ensure_m(h, m);
     if (rc) return rc;
@@ -799,6 +817,10 @@ int ekf_sharded_rows(ekf_sharded* h, int shard, int64_t* row_begin, int64_t* row
 int ekf_sharded_get_sigma_rows(ekf_sharded* h, int shard, double* out, int64_t ld) {
     if (!h || !out || shard < 0 || shard >= (int)h->sh.size() || ld < h->N) return fail(-1, "invalid argument");
     Dev g(h->device);
+    {
+        int rc_ = settle(h);
+        if (rc_) return rc_;
+    }
     Shard& s = h->sh[shard];
     if (s.rows > 0)
         CU(cudaMemcpy2DAsync(out, sizeof(double) * ld, s.sig, sizeof(double) * h->ld, sizeof(double) * h->N, s.rows,
@@ -809,10 +831,28 @@ int ekf_sharded_get_sigma_rows(ekf_sharded* h, int shard, double* out, int64_t l
 int ekf_sharded_update_count(ekf_sharded* h, uint64_t* out) {
     if (!h || !out) return fail(-1, "null argument");
     Dev g(h->device);
+    {
+        int rc_ = settle(h);
+        if (rc_) return rc_;
+    }
     unsigned long long v = 0;
     CU(cudaMemcpyAsync(&v, h->sh[0].nupd, sizeof(v), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     *out = v;
+    return 0;
+}
+int ekf_sharded_sweep_count(ekf_sharded* h, uint64_t* out) {
+    if (!h || !out) return fail(-1, "null argument");
+    *out = h->sweeps;
+    return 0;
+}
+int ekf_sharded_set_carry_pending(ekf_sharded* h, int carry) {
+    if (!h) return fail(-1, "null handle");
+    h->carry_pending = carry ? 1 : 0;
+    if (!h->carry_pending) {
+        Dev g(h->device);
+        return settle(h);
+    }
     return 0;
 }
 int ekf_sharded_launch_count(ekf_sharded* h, uint64_t* out) {
@@ -823,6 +863,10 @@ int ekf_sharded_launch_count(ekf_sharded* h, uint64_t* out) {
 int ekf_sharded_sync(ekf_sharded* h) {
     if (!h) return fail(-1, "null handle");
     Dev g(h->device);
+    {
+        int rc_ = settle(h);
+        if (rc_) return rc_;
+    }
     CU(cudaStreamSynchronize(h->stream));
     return 0;
 }
@@ -839,6 +883,10 @@ int ekf_sharded_timer_start(ekf_sharded* h) {
 int ekf_sharded_timer_stop(ekf_sharded* h, float* ms_out) {
     if (!h || !ms_out || !h->t0) return fail(-1, "timer not started");
     Dev g(h->device);
+    {
+        int rc_ = settle(h);
+        if (rc_) return rc_;
+    }
     CU(cudaEventRecord(h->t1, h->stream));
     CU(cudaEventSynchronize(h->t1));
     CU(cudaEventElapsedTime(ms_out, h->t0, h->t1));

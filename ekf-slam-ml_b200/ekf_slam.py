@@ -228,9 +228,20 @@ class EKF_SLAM:
     def sync(self):
         check(self._L.ekf_sync(self._h))
 
+    @property
+    def sweep_count(self):
+        v = ctypes.c_uint64()
+        check(self._L.ekf_sweep_count(self._h, ctypes.byref(v)))
+        return v.value
+
     def set_max_pending(self, k):
         """Streamed engine: corrections accumulated per pass over Sigma (1..8); results do not depend on it."""
         check(self._L.ekf_set_max_pending(self._h, int(k)))
+
+    def set_carry_pending(self, on):
+        """Streamed engine: let correction factors stay pending across prediction() / measurement() calls (default on;
+        off = Sigma is swept at the end of every measurement(), bit-identical to one sweep per correction)."""
+        check(self._L.ekf_set_carry_pending(self._h, 1 if on else 0))
 
     def timer_start(self):
         check(self._L.ekf_timer_start(self._h))

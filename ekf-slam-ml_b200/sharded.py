@@ -108,6 +108,16 @@ class ShardedEKF:
         _check(self._L.ekf_sharded_launch_count(self._h, ctypes.byref(v)))
         return v.value
 
+    @property
+    def sweep_count(self):
+        v = ctypes.c_uint64()
+        _check(self._L.ekf_sharded_sweep_count(self._h, ctypes.byref(v)))
+        return v.value
+
+    def set_carry_pending(self, on):
+        """Let correction factors stay pending across prediction() / measurement() calls (default on)."""
+        _check(self._L.ekf_sharded_set_carry_pending(self._h, 1 if on else 0))
+
     def sync(self):
         _check(self._L.ekf_sharded_sync(self._h))
 

@@ -42,6 +42,10 @@ int ekf_sharded_get_state(ekf_sharded* h, double* out /* N */);
 int ekf_sharded_rows(ekf_sharded* h, int shard, int64_t* row_begin, int64_t* row_end);
 int ekf_sharded_get_sigma_rows(ekf_sharded* h, int shard, double* out, int64_t ld);
 int ekf_sharded_update_count(ekf_sharded* h, uint64_t* out);
+/* As ekf_set_carry_pending / ekf_sweep_count of ekf_slam_b200.h: correction factors stay pending across prediction()
+ * and measurement() calls by default (every rank must use the same setting); verbs that read Sigma settle them. */
+int ekf_sharded_set_carry_pending(ekf_sharded* h, int carry);
+int ekf_sharded_sweep_count(ekf_sharded* h, uint64_t* out);
 int ekf_sharded_launch_count(ekf_sharded* h, uint64_t* out);
 int ekf_sharded_sync(ekf_sharded* h);
 int ekf_sharded_timer_start(ekf_sharded* h);

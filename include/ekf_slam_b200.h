@@ -94,6 +94,13 @@ int ekf_sync(ekf_filter* h);
 /* Streamed engine only: corrections accumulated before Sigma is swept (1..8, default 8).  Results are bit-identical
  * for every value; 1 reproduces the reference's schedule of one pass over Sigma per correction (ekf_slam.cpp:191-192). */
 int ekf_set_max_pending(ekf_filter* h, int max_pending);
+/* 1 (default): correction factors may stay pending across prediction() and measurement() calls (prediction() maps
+ * them through the motion Jacobian in O(1)), so every sweep of the streamed engine carries max_pending corrections;
+ * 0: Sigma is swept at the end of every measurement().  Every verb that reads Sigma or the update counter settles the
+ * pending factors first, so the difference is only visible in rounding (1e-15 relative) and in speed. */
+int ekf_set_carry_pending(ekf_filter* h, int carry);
+/* passes over Sigma the streamed engine has made so far (for the roofline accounting of bench.py) */
+int ekf_sweep_count(ekf_filter* h, uint64_t* out);
 /* raw device pointers for callers that live on the GPU already (bench, fused pipelines) */
 int ekf_device_pointers(ekf_filter* h, void** sigma, int64_t* ld, void** state);
 void* ekf_stream(ekf_filter* h); /* cudaStream_t */

@@ -448,6 +448,7 @@ def test_delayed_application_is_bit_identical(gpu_pkg):
     for k in (1, 3, 8):
         f = gpu_pkg.EKF_SLAM(n, engine=gpu_pkg.ENGINE_STREAM)
         f.set_max_pending(k)
+        f.set_carry_pending(False)  # groups end with the measurement() call
         for t in range(8):
             f.prediction(tuple(tr["twists"][t, 0]))
             f.measurement(tr["xy"][t, 0], tr["vis"][t, 0])
@@ -457,3 +458,28 @@ def test_delayed_application_is_bit_identical(gpu_pkg):
         assert np.array_equal(st.view(np.uint64), outs[0][0].view(np.uint64))
         assert np.array_equal(sg.view(np.uint64), outs[0][1].view(np.uint64))
     assert outs[2][2] < outs[0][2]  # fewer launches: fewer sweeps
+
+
+def test_pending_factors_carried_across_prediction(gpu_pkg):
+    """Default schedule of the streamed engine: factors stay pending across prediction() (mapped through the motion
+    Jacobian) and measurement() calls, so sweeps always carry max_pending corrections.  Same filter to rounding as
+    the per-call schedule and as the oracle; getters settle the pending factors."""
+    n = 300
+    tg = gpu_pkg.tracegen
+    w = tg.grid_world(20, 15, pitch=0.4, n_slots=n, max_visible=0.55)  # 4-6 visible landmarks per step
+    T = 14
+    tr = tg.simulate_known(w, 1, T, seed=23)
+    a = gpu_pkg.EKF_SLAM(n, engine=gpu_pkg.ENGINE_STREAM)
+    b = gpu_pkg.EKF_SLAM(n, engine=gpu_pkg.ENGINE_STREAM)
+    b.set_carry_pending(False)
+    o = OracleEKF(n)
+    for t in range(T):
+        for f in (a, b, o):
+            f.prediction(tuple(tr["twists"][t, 0])) if f is not o else f.prediction(*tr["twists"][t, 0])
+            f.measurement(tr["xy"][t, 0], tr["vis"][t, 0])
+        if t == T // 2:  # a getter in the middle settles the factors without changing the outcome
+            assert sigma_err(a.sigma, o.sigma) < TOL
+    assert a.sweep_count < b.sweep_count             # fewer passes over Sigma
+    assert a.update_count == b.update_count == int(tr["vis"].sum())
+    assert state_err(a.state, b.state) < 1e-12 and sigma_err(a.sigma, b.sigma) < 1e-11
+    assert state_err(a.state, o.state) < TOL and sigma_err(a.sigma, o.sigma) < TOL

@@ -144,7 +144,8 @@ cnt = sh.allreduce_sum(np.array([rows.size], dtype=np.float64), dist)
 assert int(cnt[0]) == 203
 dist.barrier()
 dist.destroy_process_group()
-print("rank", rank, "ok")
+sys.stdout.write("rank %d ok\n" % rank)  # one write: two ranks share the pipe
+sys.stdout.flush()
 '''
 
 
