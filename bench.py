@@ -621,12 +621,12 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--filters", type=int, default=FILTERS_PER_GPU, help="filters per GPU (cfg3 = 65536)")
     ap.add_argument("--large-n", type=int, default=8192)
-    ap.add_argument("--large-updates", type=int, default=200)
+    ap.add_argument("--large-updates", type=int, default=240)
     ap.add_argument("--skip-large", action="store_true")
     ap.add_argument("--only-large", action="store_true", help="profiling aid: run just the cfg4 leg")
     ap.add_argument("--only-laser", action="store_true", help="profiling aid: run just the laser front-end leg")
     ap.add_argument("--sharded-n", type=int, default=40000, help="cfg5 landmarks (square number), N>1 only")
-    ap.add_argument("--sharded-updates", type=int, default=50)
+    ap.add_argument("--sharded-updates", type=int, default=96)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)
