@@ -211,8 +211,8 @@ def large_map_leg(pkg, device, n_lm, timed_updates, peak_gbs, want_cpu):
         "roofline": {"bound": "hbm", "kernel": "k_large_sweep_tma<P> / k_large_sweep_p<P> (time per sweep = whole step incl. predict + gains)",
                      "achieved": alg_bytes * n_sweeps / (sweep_ms_total * 1e-3) / 1e9, "peak": peak_gbs, "unit": "GB/s",
                      "frac": alg_bytes * n_sweeps / (sweep_ms_total * 1e-3) / 1e9 / peak_gbs,
-                     # ncu capture profiles/r1_prof_sweep_tma_raw.csv: 2.194 GB read + 2.115 GB written per launch
-                     "traffic": 4.309e9 if n_lm == 8192 else None,
+                     # ncu capture profiles/r1_prof_sweep_tma_raw.csv (P = 12): 2.220 GB read + 2.096 GB written per launch
+                     "traffic": 4.316e9 if n_lm == 8192 else None,
                      "algorithmic_bytes_per_launch": alg_bytes, "sweeps": n_sweeps,
                      "updates_per_sweep": done / max(n_sweeps, 1),
                      "per_update_achieved": alg_bytes / (ms_upd * 1e-3) / 1e9,

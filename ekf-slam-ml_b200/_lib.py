@@ -154,6 +154,25 @@ _lib = None
 _lib_sharded = None
 
 
+def _preload_bundled_nccl():
+    """libekfslam_sharded_b200.so needs `libnccl.so.2`.  If the process later imports torch, torch insists on the NCCL
+    it was built with (a newer one than the system's), and whichever libnccl.so.2 is mapped first wins: so map the
+    wheel-bundled one first when there is one.  Without it the dynamic loader falls back to the system library."""
+    import importlib.util
+    import sys
+    if "torch" in sys.modules:
+        return  # torch already mapped its own
+    spec = importlib.util.find_spec("nvidia.nccl") if importlib.util.find_spec("nvidia") else None
+    for base in (list(spec.submodule_search_locations) if spec and spec.submodule_search_locations else []):
+        cand = os.path.join(base, "lib", "libnccl.so.2")
+        if os.path.exists(cand):
+            try:
+                ctypes.CDLL(cand, mode=ctypes.RTLD_GLOBAL)
+            except OSError:
+                pass
+            return
+
+
 def load_sharded():
     """Load the row-sharded engine's library (once).  Raises if it has not been built or NCCL cannot be resolved."""
     global _lib_sharded
@@ -161,6 +180,7 @@ def load_sharded():
         return _lib_sharded
     if not os.path.exists(SHARDED_LIB_PATH):
         raise ImportError(f"{SHARDED_LIB_PATH} is missing: run ./build.sh")
+    _preload_bundled_nccl()
     lib = ctypes.CDLL(SHARDED_LIB_PATH)
     for name, (res, args) in SIGNATURES_SHARDED.items():
         fn = getattr(lib, name)
