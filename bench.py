@@ -217,7 +217,7 @@ def large_map_leg(pkg, device, n_lm, timed_updates, peak_gbs, want_cpu):
                      "updates_per_sweep": done / max(n_sweeps, 1),
                      "per_update_achieved": alg_bytes / (ms_upd * 1e-3) / 1e9,
                      "per_update_frac": alg_bytes / (ms_upd * 1e-3) / 1e9 / peak_gbs,
-                     "note": "one launch moves Sigma once (16 N^2 B) and applies up to 12 pending corrections; per_update_* "
+                     "note": "one launch moves Sigma once (16 N^2 B) and applies up to 14 pending corrections; per_update_* "
                              "is SURVEY.md's 16 N^2-per-correction convention and exceeds 1 for that reason"},
     }
     if want_cpu:

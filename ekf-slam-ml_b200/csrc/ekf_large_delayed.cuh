@@ -11,10 +11,10 @@
 
 namespace ekf {
 
-// 12: measured optimum of the TMA sweep on B200 at N = 16,387 (per correction 0.101 ms at 8, 0.086 at 10, 0.077 at 12,
-// 0.084 at 14, 0.101 at 16: beyond 12 the consumers' W pairs no longer fit the register file)
+// 14: measured optimum of the TMA sweep on B200 at N = 16,387 (per correction, whole period: 0.101 ms at 8, 0.086 at 10,
+// 0.078 at 12, 0.073 at 14, 0.093 at 16: 2 x 16 FMAs per element no longer hide behind the copy)
 #ifndef EKF_MAX_PENDING
-#define EKF_MAX_PENDING 12
+#define EKF_MAX_PENDING 14
 #endif
 constexpr int kMaxPending = EKF_MAX_PENDING;
 

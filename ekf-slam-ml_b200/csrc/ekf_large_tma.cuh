@@ -177,24 +177,29 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
                     mbar_wait(full + stage, phase);
                     double* tile = tiles + (size_t)stage * kStageRows * kTmaCols;
                     const double2* kst = ksm + (size_t)stage * kMaxPending * kStageRows;
-                    double2 v[kStageRows];
+                    // the stage's rows go through in batches of RBN so that v[] + the 8 P registers of W pairs fit
+                    constexpr int RBN = (P > 12) ? 4 : kStageRows;
 #pragma unroll
-                    for (int k = 0; k < kStageRows; ++k) {
-                        v[k] = make_double2(0.0, 0.0);
-                        if (k < nr && has) v[k] = *reinterpret_cast<const double2*>(tile + k * kTmaCols + ca);
-                    }
+                    for (int k0 = 0; k0 < kStageRows; k0 += RBN) {
+                        double2 v[RBN];
 #pragma unroll
-                    for (int j = 0; j < P; ++j) {
-#pragma unroll
-                        for (int k = 0; k < kStageRows; ++k) {
-                            const double2 kk = kst[j * kStageRows + k];
-                            v[k].x = apply_factor(v[k].x, kk, wv[j][0]);
-                            v[k].y = apply_factor(v[k].y, kk, wv[j][1]);
+                        for (int k = 0; k < RBN; ++k) {
+                            v[k] = make_double2(0.0, 0.0);
+                            if (k0 + k < nr && has) v[k] = *reinterpret_cast<const double2*>(tile + (k0 + k) * kTmaCols + ca);
                         }
-                    }
 #pragma unroll
-                    for (int k = 0; k < kStageRows; ++k)
-                        if (k < nr && has) *reinterpret_cast<double2*>(tile + k * kTmaCols + ca) = v[k];
+                        for (int j = 0; j < P; ++j) {
+#pragma unroll
+                            for (int k = 0; k < RBN; ++k) {
+                                const double2 kk = kst[j * kStageRows + k0 + k];
+                                v[k].x = apply_factor(v[k].x, kk, wv[j][0]);
+                                v[k].y = apply_factor(v[k].y, kk, wv[j][1]);
+                            }
+                        }
+#pragma unroll
+                        for (int k = 0; k < RBN; ++k)
+                            if (k0 + k < nr && has) *reinterpret_cast<double2*>(tile + (k0 + k) * kTmaCols + ca) = v[k];
+                    }
                     fence_proxy_async_smem();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(done + stage);

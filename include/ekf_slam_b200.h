@@ -91,7 +91,7 @@ int ekf_get_init_flag(ekf_filter* h, int* out);  /* landmark_init_flag, ekf_slam
 int ekf_set_init_flag(ekf_filter* h, int v);
 int ekf_update_count(ekf_filter* h, uint64_t* out); /* landmark corrections executed so far */
 int ekf_sync(ekf_filter* h);
-/* Streamed engine only: corrections accumulated before Sigma is swept (1..12, default 12: the measured optimum of
+/* Streamed engine only: corrections accumulated before Sigma is swept (1..14, default 14: the measured optimum of
  * the sweep kernel).  Within a measurement() call the delayed application is bit-identical to one sweep per correction
  * (1 reproduces the reference's schedule); across calls see ekf_set_carry_pending. */
 int ekf_set_max_pending(ekf_filter* h, int max_pending);
