@@ -163,3 +163,29 @@ def test_two_rank_sharding_over_gloo(tmp_path):
                        capture_output=True, text=True, env=env, timeout=240)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "rank 0 ok" in r.stdout and "rank 1 ok" in r.stdout
+
+
+def test_marker_list_is_the_visible_subset_in_id_order(pkg):
+    """Host helper of ekf_batch_step_known_sparse: dense fake-sensor arrays -> CSR marker list."""
+    rng = np.random.default_rng(3)
+    B, n = 37, 23
+    xy = rng.normal(size=(B, 2 * n))
+    vis = (rng.random((B, n)) < 0.3).astype(np.uint8)
+    vis[5] = 0                                   # a robot that sees nothing
+    off, ids, pts = pkg.marker_list(xy, vis)
+    assert off.dtype == np.int32 and ids.dtype == np.uint8 and pts.dtype == np.float64 and pts.flags.c_contiguous
+    assert off[0] == 0 and off[-1] == vis.sum() == len(ids) == len(pts) and off[5] == off[6]
+    for b in range(B):
+        want = np.nonzero(vis[b])[0]
+        assert np.array_equal(ids[off[b]:off[b + 1]], want)
+        assert np.array_equal(pts[off[b]:off[b + 1]], xy[b].reshape(n, 2)[want])
+    with pytest.raises(ValueError):
+        pkg.marker_list(np.zeros((1, 600)), np.ones((1, 300), np.uint8))
+
+
+def test_accuracy_report_formatting(pkg):
+    r = {"robots": 2, "steps": 3, "seed": 0, "updates": 11, "landmark_rmse": 0.01, "landmarks": 20,
+         "rmse_xytheta": {"slam": [0.001, 0.002, 0.01], "prediction_only": [0.1, 0.2, 0.3], "wheel_odometry": [0, 0, 0]},
+         "worst_xy_error": {"slam": 0.004, "prediction_only": 0.3, "wheel_odometry": 0.0}}
+    md = pkg.report.markdown(r)
+    assert md.count("\n") >= 6 and "Slam | 0.00100 | 0.00200" in md and "Prediction only" in md
