@@ -65,7 +65,7 @@ SIGNATURES = {
     "ekf_batch_step_known_sparse": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                                    ctypes.c_void_p, ctypes.c_int64]),
     "ekf_batch_step_known_sparse_dev": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
-                                                       ctypes.c_void_p]),
+                                                       ctypes.c_void_p, ctypes.c_int64]),
     "ekf_batch_step_known_dev": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     "ekf_batch_step_unknown_dev": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                                   ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]),

@@ -1081,11 +1081,12 @@ int ekf_batch_step_known(ekf_batch* b, const double* twists, const double* xy, c
 }
 
 int ekf_batch_step_known_sparse_dev(ekf_batch* b, const double* d_twists, const int32_t* d_offsets, const uint8_t* d_ids,
-                                    const double* d_xy) {
-    if (!b || !d_twists || !d_offsets || !d_ids || !d_xy) return fail(EKF_ERR_INVALID, "null argument");
+                                    const double* d_xy, int64_t total) {
+    if (!b || !d_twists || !d_offsets || !d_ids || !d_xy || total < 0) return fail(EKF_ERR_INVALID, "invalid argument");
     DeviceGuard g(b->device);
     FusedParams p = batch_params(b, kDoPredict | kDoMeasurement | kSparseReadings, 1, d_twists, d_xy, d_ids, d_offsets,
                                  nullptr);
+    p.sparse_total = total;
     int rc = launch_fused_sym(p, b->stream, b->device);
     b->launches += 1;
     return rc;
@@ -1109,7 +1110,7 @@ int ekf_batch_step_known_sparse(ekf_batch* b, const double* twists, const int32_
     }
     CU(cudaEventRecord(b->ev_copied[s], b->copy_stream));
     CU(cudaStreamWaitEvent(b->stream, b->ev_copied[s], 0));
-    int rc = ekf_batch_step_known_sparse_dev(b, b->d_twists[s], b->d_count[s], b->d_vis[s], b->d_xy[s]);
+    int rc = ekf_batch_step_known_sparse_dev(b, b->d_twists[s], b->d_count[s], b->d_vis[s], b->d_xy[s], total);
     if (rc) return rc;
     CU(cudaEventRecord(b->ev_consumed[s], b->stream));
     return EKF_OK;

@@ -39,6 +39,7 @@ struct FusedParams {
     int mode;
     int sig_stride;  // doubles
     int st_stride;   // doubles
+    long long sparse_total;  // marker-list mode: number of listed markers (offsets are checked against it)
 };
 
 __host__ __device__ inline int fused_round16(int v) { return (v + 15) & ~15; }

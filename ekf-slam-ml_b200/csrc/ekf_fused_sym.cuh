@@ -347,6 +347,8 @@ __global__ void __launch_bounds__(32, NL == 20 ? EKF_SYM_MINB : 1) ekf_fused_sym
         // marker list: p.mcount = CSR offsets [B + 1], p.vis = landmark ids, p.xy = (x, y) per listed marker
         sp_begin = p.mcount[b];
         sp_count = p.mcount[b + 1] - sp_begin;
+        // malformed offsets must not turn into out-of-bounds reads: such a filter gets an empty list
+        if (sp_begin < 0 || sp_count < 0 || (long long)sp_begin + sp_count > p.sparse_total) sp_count = 0;
         for (int k0 = 0; k0 < sp_count; k0 += 32) {
             const int k = k0 + lane;
             const bool on = k < sp_count;

@@ -125,14 +125,15 @@ int ekf_batch_step_unknown(ekf_batch* b, const double* twists, const double* mea
 /* The same step fed with the fake_sensor message as it is on the wire: only the visible markers, each with its
  * landmark id (published at nurtlesim/src/tube_world.cpp:369-414, unpacked into the dense arrays at
  * nuslam/src/slam.cpp:232-262).  CSR: offsets [B + 1] (filter b owns entries offsets[b] .. offsets[b+1]-1, at most n,
- * ids unique within a filter), ids [total] < n, xy [total][2].  A slot that is not listed is not visible and reads
+ * ids unique within a filter), ids [total] < n, xy [total][2]; a filter whose offsets do not lie inside [0, total]
+ * gets an empty list, an id >= n is ignored.  A slot that is not listed is not visible and reads
  * (0, 0), exactly what the node's dense arrays hold for it; results are bit-identical to ekf_batch_step_known() on
  * those dense arrays, with about a third of the host-to-device bytes. */
 int ekf_batch_step_known_sparse(ekf_batch* b, const double* twists, const int32_t* offsets, const uint8_t* ids,
                                 const double* xy, int64_t total);
 /* Same verbs with inputs already resident in HBM (device pointers, same layouts). */
 int ekf_batch_step_known_sparse_dev(ekf_batch* b, const double* d_twists, const int32_t* d_offsets, const uint8_t* d_ids,
-                                    const double* d_xy);
+                                    const double* d_xy, int64_t total);
 int ekf_batch_step_known_dev(ekf_batch* b, const double* d_twists, const double* d_xy, const uint8_t* d_visible);
 int ekf_batch_step_unknown_dev(ekf_batch* b, const double* d_twists, const double* d_meas, const int32_t* d_count,
                                int m_max, int32_t* d_assoc_out);

@@ -240,6 +240,18 @@ def test_batch_marker_list_equals_dense_arrays(gpu_pkg, n):
     assert np.array_equal(sparse.states(), dense.states())
     for b in (0, B // 2, B - 1):
         assert np.array_equal(sparse.sigma(b), dense.sigma(b))
+    # malformed offsets (beyond the list, decreasing) give those filters an empty list instead of a wild read
+    bad = gpu_pkg.EKFBatch(B, n)
+    ref2 = gpu_pkg.EKFBatch(B, n)
+    off, ids, pts = gpu_pkg.marker_list(xy, vis)
+    broken = off.copy()
+    broken[3] = off[-1] + 1000       # filter 2 ends (and filter 3 starts) outside the list
+    tw0 = np.ascontiguousarray(tr["twists"][1])
+    bad.step_known_sparse(tw0, broken, ids, pts, total=int(off[-1]))
+    ref2.step_known_sparse(tw0, off, ids, pts)
+    bad.sync(), ref2.sync()
+    sb, sr = bad.states(), ref2.states()
+    assert np.all(np.isfinite(sb)) and np.array_equal(sb[4:], sr[4:]) and np.array_equal(sb[:2], sr[:2])
     # an empty list is a prediction-only step
     before = sparse.states()
     sparse.step_known_sparse(np.zeros((B, 2)), np.zeros(B + 1, np.int32), np.zeros(0, np.uint8), np.zeros((0, 2)))
