@@ -142,6 +142,7 @@ int ekf_batch_get_poses(ekf_batch* b, double* out /* [B][3] theta,x,y */);
 /* asynchronous read-back into pinned memory; complete after ekf_batch_sync() */
 int ekf_batch_get_poses_async(ekf_batch* b, double* pinned_out);
 int ekf_batch_get_states(ekf_batch* b, double* out /* [B][N] */);
+/* one filter's covariance as a dense row-major N x N matrix (expanded from the engine's symmetric storage) */
 int ekf_batch_get_sigma(ekf_batch* b, int64_t filter, double* out, int64_t ld);
 int ekf_batch_get_known(ekf_batch* b, uint8_t* out /* [B][n] */);
 int ekf_batch_set_known(ekf_batch* b, const uint8_t* in);
@@ -158,6 +159,10 @@ int ekf_batch_import(ekf_batch* b, const double* sigma, const double* state, con
  * out4 = {sum dx^2, sum dy^2, sum wrap(dtheta)^2, B} — the per-GPU partial that ranks all-reduce. */
 int ekf_batch_pose_error(ekf_batch* b, const double* truth, double* out4);
 int ekf_batch_sync(ekf_batch* b);
+/* Raw device arrays of the batch.  state: [B][state_stride] doubles (theta, x, y, m1x, m1y, ...).  sigma:
+ * [B][sigma_stride] doubles in the engine's SYMMETRIC block-staircase layout: row r stores the columns
+ * [16*floor(r/16), N) only, rows back to back (element (r, c) with c < 16*floor(r/16) is the stored (c, r)); use
+ * ekf_batch_get_sigma() for a dense copy. */
 int ekf_batch_device_pointers(ekf_batch* b, void** sigma, int64_t* sigma_stride, void** state,
                               int64_t* state_stride);
 void* ekf_batch_stream(ekf_batch* b);
