@@ -173,6 +173,10 @@ __device__ __forceinline__ void sym_rank2_blockrow(double* __restrict__ sig, con
     constexpr int BASE = stair_row_base(16 * RBK, NC);
     constexpr int RB = (CH >= 3) ? (NF == 1 ? EKF_SYM_RB3_1 : EKF_SYM_RB3_2)
                                  : (CH == 2 ? (NF == 1 ? EKF_SYM_RB2_1 : EKF_SYM_RB2_2) : EKF_SYM_RB1);
+    // Loads are unconditional: a lane beyond the row's last column or in the missing partner row of an odd block row
+    // reads a neighbouring entry of the same shared-memory allocation and its result is simply not stored.  That
+    // keeps the ragged edges (11 of 16 lanes in the last chunk, one row short in the last block row) free of
+    // branches; only the stores are predicated.
 #pragma unroll
     for (int a0 = 0; a0 < SL; a0 += RB) {
         double2 ka[RB], kb[RB];
@@ -180,25 +184,23 @@ __device__ __forceinline__ void sym_rank2_blockrow(double* __restrict__ sig, con
 #pragma unroll
         for (int u = 0; u < RB; ++u) {
             const int lr = g + 2 * (a0 + u);
-            if (a0 + u < SL && lr < ROWS) {
+            if (a0 + u < SL) {
                 ka[u] = Ka[16 * RBK + lr];
                 if (NF == 2) kb[u] = Kb[16 * RBK + lr];
 #pragma unroll
-                for (int b = 0; b < CH; ++b)
-                    if (16 * (RBK + b) + q < NC) v[u][b] = sig[BASE + lr * LROW + q + 16 * b];
+                for (int b = 0; b < CH; ++b) v[u][b] = sig[BASE + lr * LROW + q + 16 * b];
             }
         }
 #pragma unroll
         for (int u = 0; u < RB; ++u) {
             const int lr = g + 2 * (a0 + u);
-            if (a0 + u < SL && lr < ROWS) {
+            if (a0 + u < SL) {
 #pragma unroll
-                for (int b = 0; b < CH; ++b)
-                    if (16 * (RBK + b) + q < NC) {
-                        double t = apply_pair(v[u][b], ka[u], wa[RBK + b]);
-                        if (NF == 2) t = apply_pair(t, kb[u], wb[RBK + b]);
-                        sig[BASE + lr * LROW + q + 16 * b] = t;
-                    }
+                for (int b = 0; b < CH; ++b) {
+                    double t = apply_pair(v[u][b], ka[u], wa[RBK + b]);
+                    if (NF == 2) t = apply_pair(t, kb[u], wb[RBK + b]);
+                    if (lr < ROWS && 16 * (RBK + b) + q < NC) sig[BASE + lr * LROW + q + 16 * b] = t;
+                }
             }
         }
     }
