@@ -117,7 +117,8 @@ __device__ __forceinline__ void sym_warp_gain(const double* __restrict__ sig, do
 #pragma unroll
     for (int sl = 0; sl < NS; ++sl) {
         const int c = lane + 32 * sl;
-        if (c < N) {
+        // compile-time N: a lane beyond the last column reads neighbouring shared memory and stores nothing (no branch)
+        if (NL != 0 || c < N) {
             const int cm = cmv[sl];
             const bool t3 = c < b3, t4 = c < b4;
             double s0 = sig[c], s1 = sig[N + c], s2 = sig[2 * N + c];
@@ -132,7 +133,7 @@ __device__ __forceinline__ void sym_warp_gain(const double* __restrict__ sig, do
                 s4 = apply_pair(s4, t4 ? kc : ka[4], t4 ? wa4 : wc);
             }
             h_rows(h, s0, s1, s2, s3, s4, wreg[sl].x, wreg[sl].y);
-            Wout[c] = wreg[sl];
+            if (c < N) Wout[c] = wreg[sl];
         }
     }
     __syncwarp();
@@ -146,14 +147,16 @@ __device__ __forceinline__ void sym_warp_gain(const double* __restrict__ sig, do
 #pragma unroll
     for (int sl = 0; sl < NS; ++sl) {
         const int r = lane + 32 * sl;
-        if (r < N) {
+        if (NL != 0 || r < N) {
             const double2 p = wreg[sl];
             const double k0 = fma(p.y, si.i10, p.x * si.i00);
             const double k1 = fma(p.y, si.i11, p.x * si.i01);
-            Kout[r] = make_double2(k0, k1);
             double ns = st[r] + fma(k1, nu1, k0 * nu0);
             if (r == 0) ns = normalize_angle(ns);  // theta is wrapped after every correction (:187)
-            st[r] = ns;
+            if (r < N) {
+                Kout[r] = make_double2(k0, k1);
+                st[r] = ns;
+            }
         }
     }
     __syncwarp();
