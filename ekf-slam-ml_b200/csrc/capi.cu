@@ -13,6 +13,7 @@
 #include "../../include/ekf_slam_b200.h"
 #include "ekf_fused.cuh"
 #include "ekf_fused_sym.cuh"
+#include "ekf_fused_tile.cuh"
 #include "ekf_large.cuh"
 #include "ekf_large_tma.cuh"
 
@@ -114,6 +115,31 @@ int launch_fused_sym(const FusedParams& p, cudaStream_t stream, int device) {
             set0[device] = L.total;
         }
         ekf_fused_sym_kernel<0><<<(unsigned)p.B, 32, L.total, stream>>>(p);
+    }
+    CU(cudaGetLastError());
+    return EKF_OK;
+}
+
+// Batched engine at the reference's map size (n = 20): Sigma resident in registers (ekf_fused_tile.cuh).
+int launch_fused_tile(const FusedParams& p, cudaStream_t stream, int device) {
+    const tile::TileSmem L(p.m_max);
+    if (L.total > max_smem_optin(device))
+        return fail(EKF_ERR_UNSUPPORTED, "fused engine: %d B of shared memory needed for m_max=%d", L.total, p.m_max);
+    if (p.B <= 0) return EKF_OK;
+    if (p.B > 0x7fffffffLL) return fail(EKF_ERR_INVALID, "batch too large for one launch");
+    static int set_a[64] = {0}, set_m[64] = {0};
+    if (p.mode & kDoAssociation) {
+        if (set_a[device] < L.total) {
+            CU(cudaFuncSetAttribute(tile::ekf_fused_tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
+            set_a[device] = L.total;
+        }
+        tile::ekf_fused_tile_kernel<true><<<(unsigned)p.B, 32, L.total, stream>>>(p);
+    } else {
+        if (set_m[device] < L.total) {
+            CU(cudaFuncSetAttribute(tile::ekf_fused_tile_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
+            set_m[device] = L.total;
+        }
+        tile::ekf_fused_tile_kernel<false><<<(unsigned)p.B, 32, L.total, stream>>>(p);
     }
     CU(cudaGetLastError());
     return EKF_OK;
@@ -861,6 +887,7 @@ struct ekf_batch {
     long long B = 0;
     int n = 0, N = 0, device = 0;
     int sig_stride = 0, st_stride = 0;
+    bool tiled = false;  // n == 20: register-resident tile layout (ekf_fused_tile.cuh); else symmetric staircase
     cudaStream_t stream = nullptr;       // compute
     cudaStream_t copy_stream = nullptr;  // H2D of the next step's inputs
     cudaStream_t out_stream = nullptr;   // D2H of results
@@ -985,8 +1012,9 @@ int ekf_batch_create(int64_t B, int n, int device, ekf_batch** out) {
     b->n = n;
     b->N = 3 + 2 * n;
     b->device = device;
-    b->sig_stride = sym_sig_stride(b->N);
-    b->st_stride = sym_st_stride(b->N);
+    b->tiled = (n == tile::kNL);
+    b->sig_stride = b->tiled ? tile::kSigStride : sym_sig_stride(b->N);
+    b->st_stride = b->tiled ? tile::kStStride : sym_st_stride(b->N);
 #define CUB(expr)                          \
     do {                                   \
         cudaError_t e_ = (expr);           \
@@ -1023,8 +1051,11 @@ int ekf_batch_create(int64_t B, int n, int device, ekf_batch** out) {
         free_batch(b);
         return fail(EKF_ERR_INVALID, "batch too large");
     }
-    k_fused_sym_init<<<(unsigned)B, 128, 0, b->stream>>>(b->d_sigma, b->d_state, b->d_init_flag, B, b->N,
-                                                         b->sig_stride, b->st_stride);
+    if (b->tiled)
+        tile::k_fused_tile_init<<<(unsigned)B, 128, 0, b->stream>>>(b->d_sigma, b->d_state, b->d_init_flag, B);
+    else
+        k_fused_sym_init<<<(unsigned)B, 128, 0, b->stream>>>(b->d_sigma, b->d_state, b->d_init_flag, B, b->N,
+                                                             b->sig_stride, b->st_stride);
     b->launches += 1;
     CUB(cudaGetLastError());
     rc = batch_ensure_xy(b, n);
@@ -1046,7 +1077,7 @@ int ekf_batch_step_known_dev(ekf_batch* b, const double* d_twists, const double*
     if (!b || !d_twists || !d_xy || !d_visible) return fail(EKF_ERR_INVALID, "null argument");
     DeviceGuard g(b->device);
     FusedParams p = batch_params(b, kDoPredict | kDoMeasurement, 1, d_twists, d_xy, d_visible, nullptr, nullptr);
-    int rc = launch_fused_sym(p, b->stream, b->device);
+    int rc = b->tiled ? launch_fused_tile(p, b->stream, b->device) : launch_fused_sym(p, b->stream, b->device);
     b->launches += 1;
     return rc;
 }
@@ -1056,7 +1087,7 @@ int ekf_batch_step_unknown_dev(ekf_batch* b, const double* d_twists, const doubl
     if (!b || !d_twists || !d_meas || m_max <= 0) return fail(EKF_ERR_INVALID, "invalid argument");
     DeviceGuard g(b->device);
     FusedParams p = batch_params(b, kDoPredict | kDoAssociation, m_max, d_twists, d_meas, nullptr, d_count, d_assoc_out);
-    int rc = launch_fused_sym(p, b->stream, b->device);
+    int rc = b->tiled ? launch_fused_tile(p, b->stream, b->device) : launch_fused_sym(p, b->stream, b->device);
     b->launches += 1;
     return rc;
 }
@@ -1087,7 +1118,7 @@ int ekf_batch_step_known_sparse_dev(ekf_batch* b, const double* d_twists, const 
     FusedParams p = batch_params(b, kDoPredict | kDoMeasurement | kSparseReadings, 1, d_twists, d_xy, d_ids, d_offsets,
                                  nullptr);
     p.sparse_total = total;
-    int rc = launch_fused_sym(p, b->stream, b->device);
+    int rc = b->tiled ? launch_fused_tile(p, b->stream, b->device) : launch_fused_sym(p, b->stream, b->device);
     b->launches += 1;
     return rc;
 }
@@ -1179,8 +1210,12 @@ int ekf_batch_get_sigma(ekf_batch* b, int64_t filter, double* out, int64_t ld) {
     DeviceGuard g(b->device);
     // the batch keeps Sigma in the symmetric staircase layout; expand one filter's copy to dense N x N
     if (!b->d_dense) CU(cudaMalloc(&b->d_dense, sizeof(double) * (size_t)b->N * b->N));
-    k_fused_sym_unpack<<<(b->N * b->N + 255) / 256, 256, 0, b->stream>>>(b->d_sigma + (size_t)filter * b->sig_stride,
-                                                                        b->d_dense, b->N);
+    if (b->tiled)
+        tile::k_fused_tile_unpack<<<(b->N * b->N + 255) / 256, 256, 0, b->stream>>>(
+            b->d_sigma + (size_t)filter * b->sig_stride, b->d_dense);
+    else
+        k_fused_sym_unpack<<<(b->N * b->N + 255) / 256, 256, 0, b->stream>>>(b->d_sigma + (size_t)filter * b->sig_stride,
+                                                                            b->d_dense, b->N);
     CU(cudaGetLastError());
     CU(cudaMemcpy2DAsync(out, sizeof(double) * ld, b->d_dense, sizeof(double) * b->N, sizeof(double) * b->N, b->N,
                          cudaMemcpyDeviceToHost, b->stream));
