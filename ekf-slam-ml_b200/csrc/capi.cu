@@ -122,25 +122,36 @@ int launch_fused_sym(const FusedParams& p, cudaStream_t stream, int device) {
 
 // Batched engine at the reference's map size (n = 20): Sigma resident in registers (ekf_fused_tile.cuh).
 int launch_fused_tile(const FusedParams& p, cudaStream_t stream, int device) {
-    const tile::TileSmem L(p.m_max);
+    const bool assoc = (p.mode & kDoAssociation) != 0;
+    const tile::TileSmem L(p.m_max, assoc);
     if (L.total > max_smem_optin(device))
         return fail(EKF_ERR_UNSUPPORTED, "fused engine: %d B of shared memory needed for m_max=%d", L.total, p.m_max);
+    if (p.sig_stride != tile::kSigStride || p.st_stride != tile::kStStride || p.n != tile::kNL)
+        return fail(EKF_ERR_STATE, "tile engine: unexpected batch layout");
     if (p.B <= 0) return EKF_OK;
     if (p.B > 0x7fffffffLL) return fail(EKF_ERR_INVALID, "batch too large for one launch");
-    static int set_a[64] = {0}, set_m[64] = {0};
-    if (p.mode & kDoAssociation) {
-        if (set_a[device] < L.total) {
-            CU(cudaFuncSetAttribute(tile::ekf_fused_tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
-            set_a[device] = L.total;
-        }
-        tile::ekf_fused_tile_kernel<true><<<(unsigned)p.B, 32, L.total, stream>>>(p);
-    } else {
-        if (set_m[device] < L.total) {
-            CU(cudaFuncSetAttribute(tile::ekf_fused_tile_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
-            set_m[device] = L.total;
-        }
-        tile::ekf_fused_tile_kernel<false><<<(unsigned)p.B, 32, L.total, stream>>>(p);
+    // persistent warps: as many single-warp CTAs as fit the device at once, each walking filters b, b + grid, ...
+    static int sms[64] = {0}, per_sm[64][2] = {{0}}, smem_set[64][2] = {{0}};
+    const int v = assoc ? 1 : 0;
+    const void* fn = assoc ? (const void*)tile::ekf_fused_tile_kernel<true> : (const void*)tile::ekf_fused_tile_kernel<false>;
+    if (smem_set[device][v] < L.total) {
+        CU(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
+        CU(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        if (!sms[device]) CU(cudaDeviceGetAttribute(&sms[device], cudaDevAttrMultiProcessorCount, device));
+        int nb = 0;
+        if (assoc)
+            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, tile::ekf_fused_tile_kernel<true>, 32, L.total));
+        else
+            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, tile::ekf_fused_tile_kernel<false>, 32, L.total));
+        per_sm[device][v] = nb > 0 ? nb : 1;
+        smem_set[device][v] = L.total;
     }
+    const long long resident = (long long)sms[device] * per_sm[device][v];
+    const unsigned grid = (unsigned)std::min<long long>(p.B, resident);
+    if (assoc)
+        tile::ekf_fused_tile_kernel<true><<<grid, 32, L.total, stream>>>(p);
+    else
+        tile::ekf_fused_tile_kernel<false><<<grid, 32, L.total, stream>>>(p);
     CU(cudaGetLastError());
     return EKF_OK;
 }
@@ -399,7 +410,9 @@ int stream_correct(ekf_filter* h, const double* pose_src, const UpdateCmd* cmd, 
     CU(cudaGetLastError());
     std::swap(h->d_state, h->d_state_alt);
     h->pending += 1;
-    if (h->pending >= h->max_pending) return stream_flush(h, cmd ? 0 : h->pending, nullptr);
+    // a correction that data_association() may still drop (cmd != nullptr) is flushed by the caller, which passes
+    // the command block so that the sweep is skipped and the update not counted for a dropped measurement
+    if (!cmd && h->pending >= h->max_pending) return stream_flush(h, h->pending, nullptr);
     return EKF_OK;
 }
 
@@ -534,14 +547,30 @@ int ekf_clone(ekf_filter* src, ekf_filter** out) {
     if (rc) return rc;
     ekf_filter* h = *out;
     DeviceGuard g(src->device);
+    // a half-made copy must not reach the caller: any failure below destroys it and clears *out
     rc = stream_settle(src);
-    if (rc) return rc;
-    CU(cudaStreamSynchronize(src->stream));
-    CU(cudaMemcpy(h->d_sigma, src->d_sigma, sizeof(double) * (size_t)src->sig_elems, cudaMemcpyDeviceToDevice));
-    CU(cudaMemcpy(h->d_state, src->d_state, sizeof(double) * src->st_stride, cudaMemcpyDeviceToDevice));
-    CU(cudaMemcpy(h->d_init_flag, src->d_init_flag, sizeof(int32_t), cudaMemcpyDeviceToDevice));
-    CU(cudaMemcpy(h->d_nupd, src->d_nupd, sizeof(unsigned long long), cudaMemcpyDeviceToDevice));
+    cudaError_t e = cudaSuccess;
+    if (!rc) e = cudaStreamSynchronize(src->stream);
+    if (!rc && e == cudaSuccess)
+        e = cudaMemcpy(h->d_sigma, src->d_sigma, sizeof(double) * (size_t)src->sig_elems, cudaMemcpyDeviceToDevice);
+    if (!rc && e == cudaSuccess)
+        e = cudaMemcpy(h->d_state, src->d_state, sizeof(double) * src->st_stride, cudaMemcpyDeviceToDevice);
+    if (!rc && e == cudaSuccess)
+        e = cudaMemcpy(h->d_init_flag, src->d_init_flag, sizeof(int32_t), cudaMemcpyDeviceToDevice);
+    if (!rc && e == cudaSuccess)
+        e = cudaMemcpy(h->d_nupd, src->d_nupd, sizeof(unsigned long long), cudaMemcpyDeviceToDevice);
+    if (!rc && e != cudaSuccess) {
+        cudaGetLastError();
+        rc = fail((int)e, "ekf_clone: %s", cudaGetErrorString(e));
+    }
+    if (rc) {
+        free_filter(h);
+        *out = nullptr;
+        return rc;
+    }
     h->init_flag_host = src->init_flag_host;
+    h->max_pending = src->max_pending;
+    h->carry_pending = src->carry_pending;
     return EKF_OK;
 }
 
@@ -822,7 +851,7 @@ int ekf_device_pointers(ekf_filter* h, void** sigma, int64_t* ld, void** state) 
     if (state) *state = h->d_state;
     return EKF_OK;
 }
-// How many corrections the streamed engine may accumulate before it sweeps Sigma (1..8, default 8).  The result
+// How many corrections the streamed engine may accumulate before it sweeps Sigma (1..kMaxPending = 14, default 14).  The result
 // is bit-identical for every setting; 1 reproduces the reference's schedule of one full pass per correction.
 int ekf_set_max_pending(ekf_filter* h, int max_pending) {
     if (!h || max_pending < 1 || max_pending > kMaxPending) return fail(EKF_ERR_INVALID, "max_pending must be 1..%d", kMaxPending);

@@ -242,14 +242,17 @@ inline cudaError_t launch_sweep(int pending, double* sig, long long ld, int n_ro
     if (pending <= 2) return launch_sweep_p(pending, sig, ld, n_rows, Kp, Wp, row0, n_updates, n_counted, cmd, sm_count, stream);
     const long long units = ((ld + kTmaCols - 1) / kTmaCols) * ((n_rows + kUnitRows - 1) / kUnitRows);
     const unsigned grid = (unsigned)(units < sm_count ? (units < 1 ? 1 : units) : sm_count);
+    int dev = -1;
+    if (cudaGetDevice(&dev) != cudaSuccess) dev = -1;
 #define EKF_TMA_CASE(PP)                                                                                              \
     case PP: {                                                                                                        \
-        static bool attr_set = false;                                                                                 \
-        if (!attr_set) {                                                                                              \
+        /* the opt-in is per device: one flag per device, indexed by the device the launch goes to */                 \
+        static bool attr_set[64] = {false};                                                                           \
+        if (dev < 0 || dev >= 64 || !attr_set[dev]) {                                                                 \
             cudaError_t e = cudaFuncSetAttribute(k_large_sweep_tma<PP>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
                                                  kTmaSmemBytes);                                                      \
             if (e != cudaSuccess) return e;                                                                           \
-            attr_set = true;                                                                                          \
+            if (dev >= 0 && dev < 64) attr_set[dev] = true;                                                           \
         }                                                                                                             \
         k_large_sweep_tma<PP><<<grid, kTmaThreads, kTmaSmemBytes, stream>>>(sig, ld, n_rows, Kp, Wp, row0, n_updates, \
                                                                              n_counted, cmd);                        \

@@ -526,7 +526,8 @@ int correct(ekf_sharded* h, bool use_cmd, bool stale_pose, int lm, double sx, do
     }
     CU(cudaGetLastError());
     h->pending += 1;
-    if (h->pending == kMaxPending) return flush(h, use_cmd ? 0 : kMaxPending, false);
+    // a correction data_association() may still drop (use_cmd) is flushed by the caller with the command block
+    if (!use_cmd && h->pending == kMaxPending) return flush(h, kMaxPending, false);
     return 0;
 }
 
