@@ -5,7 +5,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libekfslam_b200.so")
+# EKF_B200_LIB: development aid (a differently-built copy of the same library); never a fallback
+LIB_PATH = os.environ.get("EKF_B200_LIB") or os.path.join(_HERE, "libekfslam_b200.so")
 
 c_double_p = ctypes.POINTER(ctypes.c_double)
 c_float_p = ctypes.POINTER(ctypes.c_float)

@@ -126,7 +126,8 @@ int launch_fused_tile(const FusedParams& p, cudaStream_t stream, int device) {
     const tile::TileSmem L(p.m_max, assoc);
     if (L.total > max_smem_optin(device))
         return fail(EKF_ERR_UNSUPPORTED, "fused engine: %d B of shared memory needed for m_max=%d", L.total, p.m_max);
-    if (p.sig_stride != tile::kSigStride || p.st_stride != tile::kStStride || p.n != tile::kNL)
+    if (p.sig_stride != tile::kStride || p.st_stride != tile::kStride || p.n != tile::kNL ||
+        p.state != p.sigma + tile::kStOff)
         return fail(EKF_ERR_STATE, "tile engine: unexpected batch layout");
     if (p.B <= 0) return EKF_OK;
     if (p.B > 0x7fffffffLL) return fail(EKF_ERR_INVALID, "batch too large for one launch");
@@ -953,7 +954,7 @@ int free_batch(ekf_batch* b) {
     cudaDeviceSynchronize();
     cudaFree(b->d_sigma);
     cudaFree(b->d_dense);
-    cudaFree(b->d_state);
+    if (!b->tiled) cudaFree(b->d_state);  // tiled: the state lives inside the filter's block of d_sigma
     cudaFree(b->d_init_flag);
     cudaFree(b->d_known);
     cudaFree(b->d_nupd);
@@ -1042,8 +1043,9 @@ int ekf_batch_create(int64_t B, int n, int device, ekf_batch** out) {
     b->N = 3 + 2 * n;
     b->device = device;
     b->tiled = (n == tile::kNL);
-    b->sig_stride = b->tiled ? tile::kSigStride : sym_sig_stride(b->N);
-    b->st_stride = b->tiled ? tile::kStStride : sym_st_stride(b->N);
+    // tiled: one block per filter holds Sigma (fragment layout) and the state, so that one bulk copy stages it
+    b->sig_stride = b->tiled ? tile::kStride : sym_sig_stride(b->N);
+    b->st_stride = b->tiled ? tile::kStride : sym_st_stride(b->N);
 #define CUB(expr)                          \
     do {                                   \
         cudaError_t e_ = (expr);           \
@@ -1058,7 +1060,10 @@ int ekf_batch_create(int64_t B, int n, int device, ekf_batch** out) {
     CUB(cudaStreamCreateWithFlags(&b->copy_stream, cudaStreamNonBlocking));
     CUB(cudaStreamCreateWithFlags(&b->out_stream, cudaStreamNonBlocking));
     CUB(cudaMalloc(&b->d_sigma, sizeof(double) * (size_t)b->sig_stride * B));
-    CUB(cudaMalloc(&b->d_state, sizeof(double) * (size_t)b->st_stride * B));
+    if (b->tiled)
+        b->d_state = b->d_sigma + tile::kStOff;
+    else
+        CUB(cudaMalloc(&b->d_state, sizeof(double) * (size_t)b->st_stride * B));
     CUB(cudaMalloc(&b->d_init_flag, sizeof(int32_t) * (size_t)B));
     CUB(cudaMalloc(&b->d_known, (size_t)n * B));
     CUB(cudaMalloc(&b->d_nupd, sizeof(unsigned long long)));
@@ -1081,7 +1086,7 @@ int ekf_batch_create(int64_t B, int n, int device, ekf_batch** out) {
         return fail(EKF_ERR_INVALID, "batch too large");
     }
     if (b->tiled)
-        tile::k_fused_tile_init<<<(unsigned)B, 128, 0, b->stream>>>(b->d_sigma, b->d_state, b->d_init_flag, B);
+        tile::k_fused_tile_init<<<(unsigned)B, 128, 0, b->stream>>>(b->d_sigma, b->d_init_flag, B);
     else
         k_fused_sym_init<<<(unsigned)B, 128, 0, b->stream>>>(b->d_sigma, b->d_state, b->d_init_flag, B, b->N,
                                                              b->sig_stride, b->st_stride);
@@ -1265,7 +1270,7 @@ int ekf_batch_get_known(ekf_batch* b, uint8_t* out) {
 int ekf_batch_checkpoint_size(ekf_batch* b, int64_t* sigma_doubles, int64_t* state_doubles) {
     if (!b) return fail(EKF_ERR_INVALID, "null handle");
     if (sigma_doubles) *sigma_doubles = (int64_t)b->sig_stride * b->B;
-    if (state_doubles) *state_doubles = (int64_t)b->st_stride * b->B;
+    if (state_doubles) *state_doubles = (int64_t)(b->tiled ? tile::kStLen : b->st_stride) * b->B;
     return EKF_OK;
 }
 int ekf_batch_export(ekf_batch* b, double* sigma, double* state, int32_t* init_flag, uint8_t* known, uint64_t* updates) {
@@ -1274,7 +1279,11 @@ int ekf_batch_export(ekf_batch* b, double* sigma, double* state, int32_t* init_f
     const size_t B = (size_t)b->B;
     CU(cudaStreamSynchronize(b->copy_stream));
     CU(cudaMemcpyAsync(sigma, b->d_sigma, sizeof(double) * b->sig_stride * B, cudaMemcpyDeviceToHost, b->stream));
-    CU(cudaMemcpyAsync(state, b->d_state, sizeof(double) * b->st_stride * B, cudaMemcpyDeviceToHost, b->stream));
+    if (b->tiled)  // the state sits inside the Sigma blocks; it is exported as its own compact [B][44] array as well
+        CU(cudaMemcpy2DAsync(state, sizeof(double) * tile::kStLen, b->d_state, sizeof(double) * b->st_stride,
+                             sizeof(double) * tile::kStLen, B, cudaMemcpyDeviceToHost, b->stream));
+    else
+        CU(cudaMemcpyAsync(state, b->d_state, sizeof(double) * b->st_stride * B, cudaMemcpyDeviceToHost, b->stream));
     CU(cudaMemcpyAsync(init_flag, b->d_init_flag, sizeof(int32_t) * B, cudaMemcpyDeviceToHost, b->stream));
     CU(cudaMemcpyAsync(known, b->d_known, (size_t)b->n * B, cudaMemcpyDeviceToHost, b->stream));
     unsigned long long u = 0;
@@ -1291,7 +1300,11 @@ int ekf_batch_import(ekf_batch* b, const double* sigma, const double* state, con
     CU(cudaStreamSynchronize(b->copy_stream));
     CU(cudaStreamSynchronize(b->out_stream));
     CU(cudaMemcpyAsync(b->d_sigma, sigma, sizeof(double) * b->sig_stride * B, cudaMemcpyHostToDevice, b->stream));
-    CU(cudaMemcpyAsync(b->d_state, state, sizeof(double) * b->st_stride * B, cudaMemcpyHostToDevice, b->stream));
+    if (b->tiled)
+        CU(cudaMemcpy2DAsync(b->d_state, sizeof(double) * b->st_stride, state, sizeof(double) * tile::kStLen,
+                             sizeof(double) * tile::kStLen, B, cudaMemcpyHostToDevice, b->stream));
+    else
+        CU(cudaMemcpyAsync(b->d_state, state, sizeof(double) * b->st_stride * B, cudaMemcpyHostToDevice, b->stream));
     CU(cudaMemcpyAsync(b->d_init_flag, init_flag, sizeof(int32_t) * B, cudaMemcpyHostToDevice, b->stream));
     CU(cudaMemcpyAsync(b->d_known, known, (size_t)b->n * B, cudaMemcpyHostToDevice, b->stream));
     const unsigned long long u = (unsigned long long)updates;

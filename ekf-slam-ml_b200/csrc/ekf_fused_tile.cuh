@@ -1,78 +1,92 @@
 // Engine 1c: the batched fused step at the reference's map size (n = 20 slots, N = 43; nuslam/src/slam.cpp:250)
-// with Sigma resident in REGISTERS.
+// with Sigma resident in REGISTERS and the rank-2 update on the FP64 tensor-core path (DMMA).
 //
 // Same step as ekf_fused_sym.cuh (prediction + measurement() or data_association() of one filter per warp, Sigma
 // symmetric), but the warp no longer keeps Sigma in shared memory.  ekf_fused_sym_kernel<20> was bound by the
 // shared-memory pipe (81 % of the LSU wavefront peak: 190 wavefronts per correction, of which 75 were the read +
 // write of the stored Sigma entries by the rank-2 pass and 35 the per-row K fetches).  Here
-//   * the 40 x 40 landmark block of Sigma is cut into 6 x 6 tiles (three landmarks by three landmarks); the 28 tiles
-//     of the upper block triangle live one per lane, 36 doubles in registers, for the whole step.  The rank-2 pass
-//     (the (I - K H) Sigma of ekf_slam.cpp:191-192) is 72 FMAs per lane on registers and costs 12 shared-memory
-//     loads (six K pairs by tile row, six W pairs by tile column) instead of a read-modify-write of Sigma;
+//   * the 40 x 40 landmark block of Sigma is cut into 8 x 8 blocks (four landmarks by four landmarks).  The 15 blocks
+//     of the upper block triangle live in the accumulator-fragment layout of mma.sync.m8n8k4.f64 (SASS DMMA.8x8x4):
+//     lane (g, t) = (lane / 4, lane % 4) keeps row g, columns 2t, 2t + 1 of every block, 30 doubles, for the whole
+//     step;
+//   * the rank-2 update of ekf_slam.cpp:191-192, Sigma <- Sigma - K W with K (N x 2) and W = H_j Sigma (2 x N), is a
+//     k = 2 outer product; two consecutive corrections make k = 4, i.e. exactly one DMMA per block:
+//     D = C + [-K_a | -K_b] [W_a ; W_b].  A pass for TWO corrections is 15 DMMA and ten 8-byte shared-memory loads
+//     per lane (one A fragment per block row, one B fragment per block column) instead of 2 x 72 DFMA and 2 x 12
+//     16-byte loads with a scalar tiling.  DMMA accumulates k = 0..3 as a chain of FMAs (checked bit for bit in
+//     experiments/dmma_rate.cu), so the result equals two sequential rank-2 updates exactly.  The second gain of a
+//     pair sees the first one's factor as pending (its two gathered rows take the two FMAs the pass will apply);
 //   * the three robot rows of Sigma (3 x 43) live column-distributed: lane c keeps Sigma[0..2][c] and
-//     Sigma[0..2][c + 32].  W = H_j Sigma is computed column-parallel, so the robot rows never move; only the two
-//     landmark rows 3+2i, 4+2i of the correction are gathered through shared memory (seven lanes hold them: the
-//     tile row of block i/3 and, mirrored, the tile column above it), and the landmark index picks the registers
-//     through a warp-uniform three-way branch (i % 3), never through dynamic register indexing;
-//   * HBM holds each filter in exactly that order ([36 tile slots][28 lanes] + [3][44] robot rows = 1,140 doubles =
-//     9,120 B, all of it used), so staging is 42 fully coalesced 8-byte loads and stores per lane and no copy through
-//     shared memory.
-// Shared memory per filter drops from 13.5 KB to ~6 KB (K, W, the two gathered rows, a state mirror), so residency
-// is set by the register file alone.  Per correction the warp issues ~25 shared-memory instructions instead of ~110.
+//     Sigma[0..2][c + 32].  W = H_j Sigma is computed column-parallel, so the robot rows never move; they take their
+//     part of the update right in the gain, as Sigma[r][c] -= K[c] . W[r] (the transposed product: K W = W^T S^-1 W
+//     is symmetric), which needs only values the lane already holds;
+//   * only the two landmark rows 3+2i, 4+2i of a correction are gathered through shared memory; the landmark index
+//     picks the registers through a warp-uniform five-way branch (i / 4), never through dynamic register indexing;
+//   * HBM holds each filter in exactly that order ([30 slots][32 lanes] fragments + [3][44] robot rows + [44] state
+//     = 1,136 doubles = 9,088 B, read and written once per step).  Warps are persistent; while a filter is being
+//     corrected the bulk copy engine (cp.async.bulk, SASS UBLKCP) lands the next one in shared memory.
 //
-// Sigma stays exactly symmetric above / below the tiles (mirror entries are not stored); inside a diagonal tile both
-// (r, c) and (c, r) are kept and updated like any other entry, as in the staircase layout.
+// Sigma stays exactly symmetric between blocks (mirror blocks are not stored); inside a diagonal block both (r, c)
+// and (c, r) are kept and updated like any other entry.
 //
 // Restates rigid2d/src/ekf_slam.cpp:55-106, :108-197, :200-214, :217-276, :278-402 (as ekf_fused.cuh).
 #pragma once
 #include "ekf_fused.cuh"
 
+#ifndef EKF_TILE_DBG
+#define EKF_TILE_DBG 0  // timing experiments only (results are wrong): 1 no pass, 2 no gather, 4 no H_j, 32 no corrections
+#endif
 #ifndef EKF_TILE_MINB
-#define EKF_TILE_MINB 12  // resident filters per SM the kernel is compiled for (168 registers)
+#define EKF_TILE_MINB 12  // resident filters per SM the kernel is compiled for
 #endif
 
 namespace ekf {
 namespace tile {
 
 constexpr int kNL = 20, kN = 43;
-constexpr int kNB = 7;                       // landmark blocks of three (six rows / columns); the last one holds two
-constexpr int kTiles = kNB * (kNB + 1) / 2;  // 28 tiles of the upper block triangle, one per lane
-constexpr int kTS = 6;                       // tile edge
-constexpr int kRobOff = kTS * kTS * kTiles;  // 1,008: robot rows follow the tile slots
+constexpr int kBS = 8;                        // block edge: four landmarks
+constexpr int kNB = 5;                        // 40 landmark rows / 8
+constexpr int kBlocks = kNB * (kNB + 1) / 2;  // 15 blocks of the upper block triangle
+constexpr int kRobOff = 2 * kBlocks * 32;     // 960: robot rows follow the fragments
 constexpr int kRobLd = 44;
-constexpr int kSigStride = kRobOff + 3 * kRobLd;  // 1,140 doubles per filter
-constexpr int kStStride = 44;
-constexpr int kPad = 64;  // padded length of the per-column arrays in shared memory (two slots per lane)
+constexpr int kStOff = kRobOff + 3 * kRobLd;  // 1,092: the state follows the robot rows
+constexpr int kStLen = 44;
+constexpr int kStride = kStOff + kStLen;      // 1,136 doubles per filter (Sigma and state)
+constexpr int kPad = 64;      // padded length of the per-column arrays in shared memory (two slots per lane)
+constexpr int kBufStride = 68;  // pairs between the two corrections' K / W buffers: 64 B off a multiple of 128 B, so
+                                // that the fragment loads of a half-warp (both buffers) hit distinct banks
+constexpr int kGStride = 72;    // doubles between the two gathered rows (likewise)
 
-__host__ __device__ constexpr int tile_index(int rb, int cb) { return rb * kNB - rb * (rb - 1) / 2 + (cb - rb); }
+__host__ __device__ constexpr int block_index(int I, int J) { return I * kNB - I * (I - 1) / 2 + (J - I); }
 
 // offset of Sigma(r, c) inside one filter's block, any 0 <= r, c < 43
 __host__ __device__ inline int tile_at(int r, int c) {
     if (r < 3) return kRobOff + kRobLd * r + c;
     if (c < 3) return kRobOff + kRobLd * c + r;  // mirror of a robot-row entry
-    int lr = r - 3, lc = c - 3;
-    if (lr / kTS > lc / kTS) {  // below the block diagonal: the mirror tile holds it
-        const int t = lr;
-        lr = lc;
-        lc = t;
+    int q = r - 3, p = c - 3;
+    if (q / kBS > p / kBS) {  // below the block diagonal: the mirror block holds it
+        const int t = q;
+        q = p;
+        p = t;
     }
-    return ((lr % kTS) * kTS + (lc % kTS)) * kTiles + tile_index(lr / kTS, lc / kTS);
+    const int g = q % kBS, col = p % kBS;
+    return (2 * block_index(q / kBS, p / kBS) + (col & 1)) * 32 + 4 * g + (col >> 1);
 }
 
 struct TileSmem {
-    int off_sig, off_stg, off_bar, off_g, off_w, off_k, off_st, off_cst, off_robm, off_dgm, off_z, total;
+    int off_land, off_bar, off_g, off_w, off_k, off_st, off_cst, off_robm, off_dgm, off_z, total;
     __host__ __device__ TileSmem(int m_max, bool assoc) {
         int o = 0;
-        off_sig = o, o += kSigStride * 8;  // landing buffer of the NEXT filter's Sigma (bulk copy), 9,120 B
-        off_stg = o, o += kStStride * 8;   // ... and of its state
-        off_bar = o, o += 16;              // mbarrier of that copy
-        off_g = o, o += kPad * 16;         // the correction's two landmark rows, as {Sigma[i3][c], Sigma[i4][c]}
-        off_w = o, o += kPad * 16;         // W = H_j Sigma, one pair per column
-        off_k = o, o += kPad * 16;         // K, one pair per row
-        off_st = o, o += kPad * 8;         // mirror of the state (landmark positions for the next H_j)
-        off_cst = o, o += 8 * 8;           // measurement(): entry-time pose and its sine / cosine
-        off_robm = o, o += assoc ? 3 * kPad * 8 : 0;        // association only: mirror of the robot rows
-        off_dgm = o, o += assoc ? 3 * (kNL + 1) * 8 : 0;    // association only: every landmark's 2 x 2 diagonal block
+        off_land = o, o += kStride * 8;       // landing buffer of the NEXT filter (bulk copy), 9,088 B
+        off_bar = o, o += 16;                 // mbarrier of that copy
+        off_g = o, o += 2 * kGStride * 8;     // rows 3+2i / 4+2i of the correction (index c at [c + 1]: column 3 is
+                                              // 16-B aligned for the two-column stores of the gather)
+        off_w = o, o += 2 * kBufStride * 16;  // W = H_j Sigma, one pair per column; first / second correction of a pair
+        off_k = o, o += 2 * kBufStride * 16;  // K, one pair per row; likewise
+        off_st = o, o += kPad * 8;            // mirror of the state (landmark positions for the next H_j)
+        off_cst = o, o += 8 * 8;              // measurement(): entry-time pose and its sine / cosine
+        off_robm = o, o += assoc ? 3 * kPad * 8 : 0;      // association only: mirror of the robot rows
+        off_dgm = o, o += assoc ? 3 * (kNL + 4) * 8 : 0;  // association only: every landmark's 2 x 2 diagonal block
         o = (o + 15) & ~15;
         off_z = o;
         o += 3 * (kNL > m_max ? kNL : m_max) * 8;
@@ -80,66 +94,94 @@ struct TileSmem {
     }
 };
 
-struct LaneTile {
-    int lane;
-    int rb, cb;        // tile coordinates; 15 on the four lanes without a tile
-    int row0, col0;    // first matrix row / column of the tile (0 on the lanes without a tile: loads stay in range)
-    bool has, diag;
-};
-
-// the rows 3+2i, 4+2i of Sigma -> G[c] = {Sigma[i3][c], Sigma[i4][c]} for all c
-template <int O>
-__device__ __forceinline__ void gather_tile_rows(double2* __restrict__ G, const double (&T)[kTS][kTS], const LaneTile& L,
-                                                 const bool isrow, const bool iscol) {
-    if (isrow) {
+// ---- gather: rows 3+2i, 4+2i of Sigma -> G3[c], G4[c] for all c ---------------------------------------------------
+// Landmark i sits in block row I = i / 4 at rows 2o, 2o + 1 (o = i % 4).  From the diagonal block rightwards the rows
+// are held by the lanes g = 2o (row 3+2i) and g = 2o + 1 (row 4+2i), two columns per block each; left of the diagonal
+// block they are the mirror of columns 2o, 2o + 1 of the blocks (I', I), held by the lanes t = o.
+template <int I>
+__device__ __forceinline__ void gather_block_row(double* __restrict__ G3, double* __restrict__ G4,
+                                                 const double (&C)[kBlocks][2], const int g, const int t, const int o) {
+    const bool r3 = g == 2 * o, r4 = g == 2 * o + 1;
+    if (r3 || r4) {
+        double* dst = (r3 ? G3 : G4) + 3 + 2 * t;
 #pragma unroll
-        for (int b = 0; b < kTS; ++b) G[L.col0 + b] = make_double2(T[2 * O][b], T[2 * O + 1][b]);
+        for (int J = I; J < kNB; ++J)
+            *reinterpret_cast<double2*>(dst + kBS * J) = make_double2(C[block_index(I, J)][0], C[block_index(I, J)][1]);
     }
-    if (iscol) {
+    if (I > 0 && t == o) {
 #pragma unroll
-        for (int a = 0; a < kTS; ++a) G[L.row0 + a] = make_double2(T[a][2 * O], T[a][2 * O + 1]);
+        for (int Ip = 0; Ip < I; ++Ip) {
+            G3[3 + kBS * Ip + g] = C[block_index(Ip, I)][0];
+            G4[3 + kBS * Ip + g] = C[block_index(Ip, I)][1];
+        }
     }
 }
 
-__device__ __forceinline__ void gather_rows(double2* __restrict__ G, const double (&T)[kTS][kTS],
-                                            const double (&rob)[3][2], const LaneTile& L, const int i) {
-    const int bi = i / 3, off = i - 3 * bi;  // warp-uniform
+__device__ __forceinline__ void gather_rows(double* __restrict__ G3, double* __restrict__ G4,
+                                            const double (&C)[kBlocks][2], const double (&rob)[3][2], const int lane,
+                                            const int i) {
+    if (EKF_TILE_DBG & 2) return;
+    const int I = i >> 2, o = i & 3;  // warp-uniform
     const int i3 = 3 + 2 * i, i4 = i3 + 1;
     // columns 0..2 of the two rows are the mirror of the robot rows at columns i3, i4
-    const bool m3 = L.lane == (i3 & 31), m4 = L.lane == (i4 & 31);
+    const bool m3 = lane == (i3 & 31), m4 = lane == (i4 & 31);
     if (m3 || m4) {
         const bool hi = (m3 ? i3 : i4) >= 32;
-        double* dst = reinterpret_cast<double*>(G) + (m3 ? 0 : 1);
+        double* dst = m3 ? G3 : G4;
 #pragma unroll
-        for (int r = 0; r < 3; ++r) dst[2 * r] = hi ? rob[r][1] : rob[r][0];
+        for (int r = 0; r < 3; ++r) dst[r] = hi ? rob[r][1] : rob[r][0];
     }
-    const bool isrow = L.rb == bi, iscol = (L.cb == bi) && !isrow;
-    if (off == 0)
-        gather_tile_rows<0>(G, T, L, isrow, iscol);
-    else if (off == 1)
-        gather_tile_rows<1>(G, T, L, isrow, iscol);
-    else
-        gather_tile_rows<2>(G, T, L, isrow, iscol);
+    const int g = lane >> 2, t = lane & 3;
+    switch (I) {
+        case 0: gather_block_row<0>(G3, G4, C, g, t, o); break;
+        case 1: gather_block_row<1>(G3, G4, C, g, t, o); break;
+        case 2: gather_block_row<2>(G3, G4, C, g, t, o); break;
+        case 3: gather_block_row<3>(G3, G4, C, g, t, o); break;
+        default: gather_block_row<4>(G3, G4, C, g, t, o); break;
+    }
 }
 
-// Gain of one correction: W = H_j Sigma (column-parallel: robot rows from registers, landmark rows from G),
-// S = W H_j^T + R, K = W^T S^-1, state += K nu.  Leaves K and W in shared memory and this lane's W pairs in wown.
-template <class H>
-__device__ __forceinline__ void gain(const double2* __restrict__ G, double2* __restrict__ W2, double2* __restrict__ K2,
-                                     double* __restrict__ st, const double (&rob)[3][2], double (&stl)[2],
-                                     double2 (&wown)[2], const int lane, const int i, const H h, const double nu0,
-                                     const double nu1) {
+// ---- one landmark correction (ekf_slam.cpp:138-192) around the warp's shared-memory exchanges ---------------------
+// phase 1: W = H_j Sigma, column-parallel (robot rows from registers, the two landmark rows from G3 / G4).  With PEND
+// the landmark blocks still lack the factor of the pair's first correction (Kpend, this lane's W pairs in wpend): the
+// gathered entries take the two FMAs the pass will apply to them.  Columns 0..2 of the gathered rows come from the
+// robot rows, which are always up to date.
+template <bool PEND, class H>
+__device__ __forceinline__ void gain_w(const double* __restrict__ G3, const double* __restrict__ G4,
+                                       double2* __restrict__ Wcur, const double2* __restrict__ Kpend,
+                                       const double (&rob)[3][2], const double2 (&wpend)[2], double2 (&wown)[2],
+                                       const int lane, const int i, const H h) {
     const int i3 = 3 + 2 * i, i4 = i3 + 1;
-    __syncwarp();  // gathered rows are in place
+    __syncwarp();  // gathered rows (and the pending K) are in place
+    double2 kp3 = make_double2(0.0, 0.0), kp4 = kp3;
+    if (PEND) kp3 = Kpend[i3], kp4 = Kpend[i4];
 #pragma unroll
     for (int s = 0; s < 2; ++s) {
         const int c = lane + 32 * s;
-        const double2 g = G[c];
-        h_rows(h, rob[0][s], rob[1][s], rob[2][s], g.x, g.y, wown[s].x, wown[s].y);
-        W2[c] = wown[s];
+        double s3 = G3[c], s4 = G4[c];
+        if (PEND) {
+            const double f3 = apply_pair(s3, kp3, wpend[s]), f4 = apply_pair(s4, kp4, wpend[s]);
+            const bool robot_col = s == 0 && lane < 3;
+            s3 = robot_col ? s3 : f3;
+            s4 = robot_col ? s4 : f4;
+        }
+        double2 w;
+        h_rows(h, rob[0][s], rob[1][s], rob[2][s], s3, s4, w.x, w.y);
+        wown[s] = w;
+        Wcur[c] = w;
     }
     __syncwarp();
-    const double2 w0 = W2[0], w1 = W2[1], w2 = W2[2], w3 = W2[i3], w4 = W2[i4];
+}
+
+// phase 2: S = W H_j^T + R, K = W^T S^-1, state += K nu, and the robot rows' part of Sigma <- Sigma - K W.
+// Leaves K in Kcur and the new state in st.
+template <class H>
+__device__ __forceinline__ void gain_k(const double2* __restrict__ Wcur, double2* __restrict__ Kcur,
+                                       double* __restrict__ st, double (&rob)[3][2], double (&stl)[2],
+                                       const double2 (&wown)[2], const int lane, const int i, const H h, const double nu0,
+                                       const double nu1) {
+    const int i3 = 3 + 2 * i, i4 = i3 + 1;
+    const double2 w0 = Wcur[0], w1 = Wcur[1], w2 = Wcur[2], w3 = Wcur[i3], w4 = Wcur[i4];
     double s00, s01, s10, s11;
     h_rows(h, w0.x, w1.x, w2.x, w3.x, w4.x, s00, s01);
     h_rows(h, w0.y, w1.y, w2.y, w3.y, w4.y, s10, s11);
@@ -149,9 +191,8 @@ __device__ __forceinline__ void gain(const double2* __restrict__ G, double2* __r
     for (int s = 0; s < 2; ++s) {
         const int c = lane + 32 * s;
         const double2 pw = wown[s];
-        const double k0 = fma(pw.y, si.i10, pw.x * si.i00);
-        const double k1 = fma(pw.y, si.i11, pw.x * si.i01);
-        double ns = stl[s] + fma(k1, nu1, k0 * nu0);
+        const double2 k = make_double2(fma(pw.y, si.i10, pw.x * si.i00), fma(pw.y, si.i11, pw.x * si.i01));
+        double ns = stl[s] + fma(k.y, nu1, k.x * nu0);
         if (s == 0) {
             // theta (lane 0) is wrapped after every correction (:187): normalize_angle's |rad| < 2 pi path as selects
             raw0 = ns;
@@ -161,8 +202,13 @@ __device__ __forceinline__ void gain(const double2* __restrict__ G, double2* __r
             ns = (lane == 0) ? ang : ns;
         }
         stl[s] = ns;
-        K2[c] = make_double2(k0, k1);
+        Kcur[c] = k;
         st[c] = ns;
+        // Sigma[r][c] -= K[c] . W[r], r = 0..2: the transpose of the reference's K[r] . W[c] (same value: K W is
+        // symmetric), from this lane's own K pair and the W pairs already fetched for S
+        rob[0][s] = apply_pair(rob[0][s], k, w0);
+        rob[1][s] = apply_pair(rob[1][s], k, w1);
+        rob[2][s] = apply_pair(rob[2][s], k, w2);
     }
     if (lane == 0 && !(fabs(raw0) < kTwoPi)) {  // never on a sane filter
         stl[0] = normalize_angle_large(raw0);
@@ -171,27 +217,34 @@ __device__ __forceinline__ void gain(const double2* __restrict__ G, double2* __r
     __syncwarp();
 }
 
-// Sigma <- Sigma - K W on this lane's registers ((I - K H_j) Sigma, ekf_slam.cpp:191-192)
-__device__ __forceinline__ void rank2(double (&T)[kTS][kTS], double (&rob)[3][2], const double2* __restrict__ K2,
-                                      const double2* __restrict__ W2, const double2 (&wown)[2], const LaneTile& L) {
-    double2 w[kTS];
+// Sigma <- Sigma - K_a W_a [- K_b W_b] on the landmark blocks: one DMMA.8x8x4 per block with A = [-K_a | -K_b] rows of
+// the block row (k = 0, 1: first correction; k = 2, 3: second) and B = [W_a ; W_b] columns of the block column.
+// Lane (g, t) supplies A[g][t] and B[t][g].  Kab / Wab: the two corrections' buffers, kBufStride pairs apart.
+template <bool PAIR>
+__device__ __forceinline__ void pass_blocks(double (&C)[kBlocks][2], const double2* __restrict__ Kab,
+                                            const double2* __restrict__ Wab, const int lane) {
+    if (EKF_TILE_DBG & 1) return;
+    const int g = lane >> 2, t = lane & 3;
+    // element (3 + 8 I + g) of correction t / 2, component t % 2, as a double index into the pair arrays
+    const int off = 2 * (kBufStride * (t >> 1) + 3 + g) + (t & 1);
+    const double* ka = reinterpret_cast<const double*>(Kab) + off;
+    const double* wb = reinterpret_cast<const double*>(Wab) + off;
+    double a[kNB], b[kNB];
 #pragma unroll
-    for (int b = 0; b < kTS; ++b) w[b] = W2[L.col0 + b];
-#pragma unroll
-    for (int a = 0; a < kTS; ++a) {
-        const double2 k = K2[L.row0 + a];
-#pragma unroll
-        for (int b = 0; b < kTS; ++b) T[a][b] = apply_pair(T[a][b], k, w[b]);
+    for (int I = 0; I < kNB; ++I) {
+        a[I] = (PAIR || t < 2) ? -ka[2 * kBS * I] : 0.0;
+        b[I] = (PAIR || t < 2) ? wb[2 * kBS * I] : 0.0;
     }
 #pragma unroll
-    for (int r = 0; r < 3; ++r) {
-        const double2 k = K2[r];
+    for (int I = 0; I < kNB; ++I)
 #pragma unroll
-        for (int s = 0; s < 2; ++s) rob[r][s] = apply_pair(rob[r][s], k, wown[s]);
-    }
+        for (int J = I; J < kNB; ++J)
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                         : "+d"(C[block_index(I, J)][0]), "+d"(C[block_index(I, J)][1])
+                         : "d"(a[I]), "d"(b[J]));
 }
 
-// ---- H_j / nu of a known landmark without a branch (so that ptxas can interleave it with the rank-2 pass) --------
+// ---- H_j / nu of a known landmark without a branch (so that ptxas can interleave it with the pass) ----------------
 // rsqrt(d) as the CUDA library computes it in the normal range (MUFU.RSQ64H seed + one third-order step), without the
 // library's branch for zero / subnormal / infinite / NaN arguments: those set `special` and the caller redoes the
 // whole thing out of line with the library routines.
@@ -282,12 +335,12 @@ template <bool ASSOC>
 __global__ void __launch_bounds__(32, EKF_TILE_MINB) ekf_fused_tile_kernel(const FusedParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const TileSmem S(p.m_max, ASSOC);
-    double* buf_sig = reinterpret_cast<double*>(smem_raw + S.off_sig);
-    double* buf_st = reinterpret_cast<double*>(smem_raw + S.off_stg);
+    double* land = reinterpret_cast<double*>(smem_raw + S.off_land);
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + S.off_bar);
-    double2* G = reinterpret_cast<double2*>(smem_raw + S.off_g);
-    double2* W2 = reinterpret_cast<double2*>(smem_raw + S.off_w);
-    double2* K2 = reinterpret_cast<double2*>(smem_raw + S.off_k);
+    double* G3 = reinterpret_cast<double*>(smem_raw + S.off_g) + 1;
+    double* G4 = G3 + kGStride;
+    double2* Wab = reinterpret_cast<double2*>(smem_raw + S.off_w);
+    double2* Kab = reinterpret_cast<double2*>(smem_raw + S.off_k);
     double* st = reinterpret_cast<double*>(smem_raw + S.off_st);
     double* cst = reinterpret_cast<double*>(smem_raw + S.off_cst);
     double* robm = reinterpret_cast<double*>(smem_raw + S.off_robm);
@@ -296,37 +349,20 @@ __global__ void __launch_bounds__(32, EKF_TILE_MINB) ekf_fused_tile_kernel(const
 
     constexpr unsigned kFull = 0xffffffffu;
     constexpr int n = kNL;
-    constexpr uint32_t kStageBytes = (kSigStride + kStStride) * 8;
+    constexpr uint32_t kStageBytes = kStride * 8;
     const int lane = threadIdx.x;
     const long long stride_b = gridDim.x;
     long long b = blockIdx.x;
     if (b >= p.B) return;
 
-    LaneTile L;
-    L.lane = lane;
-    L.has = lane < kTiles;
-    {
-        int rb = 0, rem = lane;
-        while (rb < kNB && rem >= kNB - rb) {
-            rem -= kNB - rb;
-            ++rb;
-        }
-        L.rb = L.has ? rb : 15;
-        L.cb = L.has ? rb + rem : 15;
-        L.row0 = L.has ? 3 + kTS * L.rb : 0;
-        L.col0 = L.has ? 3 + kTS * L.cb : 0;
-        L.diag = L.has && L.rb == L.cb;
-    }
-
     if (lane == 0) {
         mbar_init(bar, 1);
         fence_mbar_init();
         mbar_arrive_expect_tx(bar, kStageBytes);
-        bulk_g2s(buf_sig, p.sigma + b * (long long)kSigStride, kSigStride * 8, bar);
-        bulk_g2s(buf_st, p.state + b * (long long)kStStride, kStStride * 8, bar);
+        bulk_g2s(land, p.sigma + b * (long long)kStride, kStageBytes, bar);
     }
     // padded tails of the per-column arrays stay zero for the whole launch
-    G[lane] = G[lane + 32] = make_double2(0.0, 0.0);
+    G3[lane] = G3[lane + 32] = G4[lane] = G4[lane + 32] = 0.0;
     uint32_t phase = 0;
     int n_corr = 0;
 
@@ -334,7 +370,8 @@ __global__ void __launch_bounds__(32, EKF_TILE_MINB) ekf_fused_tile_kernel(const
         const long long bn = b + stride_b;
         const bool more = bn < p.B;
 
-        // ---- this filter's inputs (in L2 already, thanks to the previous iteration's prefetch)
+        // ---- this filter's inputs (in L2 already, thanks to the previous iteration's prefetch); every load is issued
+        // before the first use
         double dtheta = 0.0, dxv = 0.0;
         if (p.mode & kDoPredict) {
             dtheta = p.twists[2 * b];
@@ -355,9 +392,9 @@ __global__ void __launch_bounds__(32, EKF_TILE_MINB) ekf_fused_tile_kernel(const
                 const bool on = k < sp_count;
                 int id = 0;
                 if (on) {
+                    const double sx = p.xy[2 * (long long)(sp_begin + k)], sy = p.xy[2 * (long long)(sp_begin + k) + 1];
                     id = p.vis[sp_begin + k];
-                    const Reading z =
-                        make_reading(p.xy[2 * (long long)(sp_begin + k)], p.xy[2 * (long long)(sp_begin + k) + 1]);
+                    const Reading z = make_reading(sx, sy);
                     if (id < n) {
                         zbuf[3 * id] = z.zr;
                         zbuf[3 * id + 1] = z.ux;
@@ -367,9 +404,12 @@ __global__ void __launch_bounds__(32, EKF_TILE_MINB) ekf_fused_tile_kernel(const
                 vismask |= __reduce_or_sync(kFull, (on && id < n) ? 1u << id : 0u);
             }
         } else if (!ASSOC && (p.mode & kDoMeasurement)) {
-            vismask = __ballot_sync(kFull, lane < n && p.vis[b * n + (lane < n ? lane : 0)] != 0);
+            const int ls = lane < n ? lane : 0;
+            const double sx = p.xy[b * 2 * n + 2 * ls], sy = p.xy[b * 2 * n + 2 * ls + 1];
+            const uint8_t vb = p.vis[b * n + ls];
+            vismask = __ballot_sync(kFull, lane < n && vb != 0);
             if (lane < n) {  // range and unit direction of every slot's reading (ekf_slam.cpp:140-146)
-                const Reading z = make_reading(p.xy[b * 2 * n + 2 * lane], p.xy[b * 2 * n + 2 * lane + 1]);
+                const Reading z = make_reading(sx, sy);
                 zbuf[3 * lane] = z.zr;
                 zbuf[3 * lane + 1] = z.ux;
                 zbuf[3 * lane + 2] = z.uy;
@@ -389,28 +429,28 @@ __global__ void __launch_bounds__(32, EKF_TILE_MINB) ekf_fused_tile_kernel(const
         // ---- this filter's Sigma and state: landing buffer -> registers (lane-major, conflict-free)
         mbar_wait(bar, phase);
         phase ^= 1u;
-        double T[kTS][kTS], rob[3][2], stl[2];
+        double C[kBlocks][2], rob[3][2], stl[2];
 #pragma unroll
-        for (int a = 0; a < kTS; ++a)
-#pragma unroll
-            for (int c = 0; c < kTS; ++c) T[a][c] = L.has ? buf_sig[(a * kTS + c) * kTiles + lane] : 0.0;
+        for (int k = 0; k < kBlocks; ++k) {
+            C[k][0] = land[(2 * k) * 32 + lane];
+            C[k][1] = land[(2 * k + 1) * 32 + lane];
+        }
 #pragma unroll
         for (int r = 0; r < 3; ++r) {
-            rob[r][0] = buf_sig[kRobOff + kRobLd * r + lane];
-            rob[r][1] = lane < kN - 32 ? buf_sig[kRobOff + kRobLd * r + 32 + lane] : 0.0;
+            rob[r][0] = land[kRobOff + kRobLd * r + lane];
+            rob[r][1] = lane < kN - 32 ? land[kRobOff + kRobLd * r + 32 + lane] : 0.0;
         }
-        stl[0] = buf_st[lane];
-        stl[1] = lane < kN - 32 ? buf_st[32 + lane] : 0.0;
+        stl[0] = land[kStOff + lane];
+        stl[1] = lane < kN - 32 ? land[kStOff + 32 + lane] : 0.0;
         bool staged_next = false;
-        // Issued once every register loaded above has been consumed (after the first rank-2 pass, or after the
-        // write-back of a filter without corrections): the copy engine may then overwrite the landing buffer.
+        // Issued once every register loaded above has been consumed (after the first pass, or after the write-back
+        // of a filter without corrections): the copy engine may then overwrite the landing buffer.
         auto stage_next = [&]() {
             __syncwarp();
             if (more) {
                 if (lane == 0) {
                     mbar_arrive_expect_tx(bar, kStageBytes);
-                    bulk_g2s(buf_sig, p.sigma + bn * (long long)kSigStride, kSigStride * 8, bar);
-                    bulk_g2s(buf_st, p.state + bn * (long long)kStStride, kStStride * 8, bar);
+                    bulk_g2s(land, p.sigma + bn * (long long)kStride, kStageBytes, bar);
                 }
                 // the next filter's inputs -> L2
                 if (ASSOC) {
@@ -460,7 +500,7 @@ __global__ void __launch_bounds__(32, EKF_TILE_MINB) ekf_fused_tile_kernel(const
         st[lane + 32] = stl[1];
         __syncwarp();
 
-        double2 wown[2];
+        double2 wa[2], wb[2];  // this lane's W pairs of the pair's first / second correction
 
         // ---- measurement(): known association (ekf_slam.cpp:108-197)
         if (!ASSOC && (p.mode & kDoMeasurement)) {
@@ -499,32 +539,54 @@ __global__ void __launch_bounds__(32, EKF_TILE_MINB) ekf_fused_tile_kernel(const
             if (lane == 0) {
                 cst[0] = theta, cst[1] = x, cst[2] = y, cst[3] = sth, cst[4] = cth;
             }
-            unsigned rem = vismask;
-            Innov h;
+            unsigned rem = (EKF_TILE_DBG & 32) ? 0u : vismask;
             if (rem) {
-                const int i0 = __ffs(rem) - 1;
-                h = make_innov(st[3 + 2 * i0], st[4 + 2 * i0], theta, sth, cth, x, y,
-                               Reading{zbuf[3 * i0], zbuf[3 * i0 + 1], zbuf[3 * i0 + 2]});
-                gather_rows(G, T, rob, L, i0);
-            }
-            while (rem) {
-                const int ic = __ffs(rem) - 1;
+                // Visible landmarks go through in PAIRS: both gains first (the second sees the first one's factor as
+                // pending), then ONE DMMA pass applies both rank-2 updates; H_j / nu of the next pair's first
+                // landmark are evaluated in the same basic block as the pass, without a branch, so that the scalar
+                // chain and the tensor pipe overlap.
+                int ia = __ffs(rem) - 1;
                 rem &= rem - 1;
-                gain(G, W2, K2, st, rob, stl, wown, lane, ic, h, h.nu0, h.nu1);
-                ++n_corr;
-                // H_j / nu of the next landmark depend on the state just written.  They are evaluated without a
-                // branch, in one basic block with the pass, so that the scalar chain overlaps the pass's FMAs (after
-                // the last correction the values are simply not used).
-                const int in = rem ? __ffs(rem) - 1 : ic;
-                bool slow;
-                h = make_innov_nobranch(st[3 + 2 * in], st[4 + 2 * in], cst[3], cst[4], cst[1], cst[2],
-                                        Reading{zbuf[3 * in], zbuf[3 * in + 1], zbuf[3 * in + 2]}, slow);
-                rank2(T, rob, K2, W2, wown, L);
-                if (slow)
-                    h = make_innov_cold(st[3 + 2 * in], st[4 + 2 * in], cst[0], cst[3], cst[4], cst[1], cst[2], zbuf[3 * in],
-                                        zbuf[3 * in + 1], zbuf[3 * in + 2]);
+                Innov h = make_innov(st[3 + 2 * ia], st[4 + 2 * ia], theta, sth, cth, x, y,
+                                     Reading{zbuf[3 * ia], zbuf[3 * ia + 1], zbuf[3 * ia + 2]});
+                gather_rows(G3, G4, C, rob, lane, ia);
+                for (;;) {
+                    gain_w<false>(G3, G4, Wab, nullptr, rob, wa, wa, lane, ia, h);
+                    gain_k(Wab, Kab, st, rob, stl, wa, lane, ia, h, h.nu0, h.nu1);
+                    ++n_corr;
+                    if (!rem) {  // odd count: the last correction goes through alone
+                        pass_blocks<false>(C, Kab, Wab, lane);
+                        break;
+                    }
+                    const int ib = __ffs(rem) - 1;
+                    rem &= rem - 1;
+                    gather_rows(G3, G4, C, rob, lane, ib);  // rows of the blocks that still lack the first factor
+                    bool slow = false;
+                    if (!(EKF_TILE_DBG & 4))
+                        h = make_innov_nobranch(st[3 + 2 * ib], st[4 + 2 * ib], cst[3], cst[4], cst[1], cst[2],
+                                                Reading{zbuf[3 * ib], zbuf[3 * ib + 1], zbuf[3 * ib + 2]}, slow);
+                    if (slow)
+                        h = make_innov_cold(st[3 + 2 * ib], st[4 + 2 * ib], cst[0], cst[3], cst[4], cst[1], cst[2],
+                                            zbuf[3 * ib], zbuf[3 * ib + 1], zbuf[3 * ib + 2]);
+                    gain_w<true>(G3, G4, Wab + kBufStride, Kab, rob, wa, wb, lane, ib, h);
+                    gain_k(Wab + kBufStride, Kab + kBufStride, st, rob, stl, wb, lane, ib, h, h.nu0, h.nu1);
+                    ++n_corr;
+                    // next pair's first landmark (after the last correction the values are simply not used)
+                    ia = rem ? __ffs(rem) - 1 : ib;
+                    slow = false;
+                    if (!(EKF_TILE_DBG & 4))
+                        h = make_innov_nobranch(st[3 + 2 * ia], st[4 + 2 * ia], cst[3], cst[4], cst[1], cst[2],
+                                                Reading{zbuf[3 * ia], zbuf[3 * ia + 1], zbuf[3 * ia + 2]}, slow);
+                    pass_blocks<true>(C, Kab, Wab, lane);
+                    if (!rem) break;
+                    rem &= rem - 1;
+                    if (slow)
+                        h = make_innov_cold(st[3 + 2 * ia], st[4 + 2 * ia], cst[0], cst[3], cst[4], cst[1], cst[2],
+                                            zbuf[3 * ia], zbuf[3 * ia + 1], zbuf[3 * ia + 2]);
+                    if (!staged_next) stage_next();  // every register loaded from the landing buffer has been used
+                    gather_rows(G3, G4, C, rob, lane, ia);
+                }
                 if (!staged_next) stage_next();
-                if (rem) gather_rows(G, T, rob, L, in);
             }
         }
 
@@ -539,6 +601,7 @@ __global__ void __launch_bounds__(32, EKF_TILE_MINB) ekf_fused_tile_kernel(const
             }
             const int known_count0 = known_count;
             bool mirrors_stale = true;
+            const int g = lane >> 2, t = lane & 3;
             for (int j = 0; j < m; ++j) {
                 if (mirrors_stale) {  // the distances read the robot rows and the landmarks' diagonal blocks
 #pragma unroll
@@ -546,12 +609,16 @@ __global__ void __launch_bounds__(32, EKF_TILE_MINB) ekf_fused_tile_kernel(const
                         robm[r * kPad + lane] = rob[r][0];
                         robm[r * kPad + lane + 32] = rob[r][1];
                     }
-                    if (L.diag) {
+                    if ((g >> 1) == t) {  // landmark 4 I + t of diagonal block I: rows 2t, 2t + 1, columns 2t, 2t + 1
 #pragma unroll
-                        for (int o = 0; o < 3; ++o) {
-                            dgm[3 * (3 * L.rb + o)] = T[2 * o][2 * o];
-                            dgm[3 * (3 * L.rb + o) + 1] = T[2 * o][2 * o + 1];
-                            dgm[3 * (3 * L.rb + o) + 2] = T[2 * o + 1][2 * o + 1];
+                        for (int I = 0; I < kNB; ++I) {
+                            double* d = dgm + 3 * (4 * I + t);
+                            if (g & 1) {
+                                d[2] = C[block_index(I, I)][1];
+                            } else {
+                                d[0] = C[block_index(I, I)][0];
+                                d[1] = C[block_index(I, I)][1];
+                            }
                         }
                     }
                     __syncwarp();
@@ -615,10 +682,11 @@ __global__ void __launch_bounds__(32, EKF_TILE_MINB) ekf_fused_tile_kernel(const
                 if (min_d < kGateUpdate) {  // :330
                     const double th_l = st[0], x_l = st[1], y_l = st[2];  // live pose (:331-333)
                     const Hj h = make_hj(st[3 + 2 * min_idx], st[4 + 2 * min_idx], th_l, x_l, y_l);
-                    gather_rows(G, T, rob, L, min_idx);
-                    gain(G, W2, K2, st, rob, stl, wown, lane, min_idx, h, __dsub_rn(zr, h.zr),
-                         normalize_angle(__dsub_rn(zphi, h.zphi)));  // :182-183
-                    rank2(T, rob, K2, W2, wown, L);  // the next distances need the new Sigma
+                    gather_rows(G3, G4, C, rob, lane, min_idx);
+                    gain_w<false>(G3, G4, Wab, nullptr, rob, wa, wa, lane, min_idx, h);
+                    gain_k(Wab, Kab, st, rob, stl, wa, lane, min_idx, h, __dsub_rn(zr, h.zr),
+                           normalize_angle(__dsub_rn(zphi, h.zphi)));  // :182-183
+                    pass_blocks<false>(C, Kab, Wab, lane);  // the next distances need the new Sigma
                     __syncwarp();
                     if (!staged_next) stage_next();
                     mirrors_stale = true;
@@ -643,40 +711,37 @@ __global__ void __launch_bounds__(32, EKF_TILE_MINB) ekf_fused_tile_kernel(const
         }
 
         // ---- write back: registers -> HBM, same lane-major order
-        double* go = p.sigma + b * (long long)kSigStride;
-        double* g_st = p.state + b * (long long)kStStride;
-        if (L.has) {
+        double* go = p.sigma + b * (long long)kStride;
 #pragma unroll
-            for (int a = 0; a < kTS; ++a)
-#pragma unroll
-                for (int c = 0; c < kTS; ++c) __stcs(go + (a * kTS + c) * kTiles + lane, T[a][c]);
+        for (int k = 0; k < kBlocks; ++k) {
+            __stcs(go + (2 * k) * 32 + lane, C[k][0]);
+            __stcs(go + (2 * k + 1) * 32 + lane, C[k][1]);
         }
 #pragma unroll
         for (int r = 0; r < 3; ++r) {
             __stcs(go + kRobOff + kRobLd * r + lane, rob[r][0]);
             if (lane < kN - 32) __stcs(go + kRobOff + kRobLd * r + 32 + lane, rob[r][1]);
         }
-        __stcs(g_st + lane, stl[0]);
-        if (lane < kN - 32) __stcs(g_st + 32 + lane, stl[1]);
+        __stcs(go + kStOff + lane, stl[0]);
+        if (lane < kN - 32) __stcs(go + kStOff + 32 + lane, stl[1]);
         if (lane == 0) p.init_flag[b] = init_flag;
         if (!staged_next) stage_next();
     }
     if (lane == 0 && p.n_updates && n_corr) atomicAdd(p.n_updates, (unsigned long long)n_corr);
 }
 
-// Sigma_0 = blockdiag(0_3, 100 I) in the tile layout (ekf_slam.cpp:36-47), zero state, init flag cleared.
-__global__ void k_fused_tile_init(double* sigma, double* state, int32_t* init_flag, long long B) {
+// Sigma_0 = blockdiag(0_3, 100 I) in the fragment layout (ekf_slam.cpp:36-47), zero state, init flag cleared.
+__global__ void k_fused_tile_init(double* sigma, int32_t* init_flag, long long B) {
     const long long b = blockIdx.x;
     if (b >= B) return;
-    double* s = sigma + b * (long long)kSigStride;
-    for (int e = threadIdx.x; e < kSigStride; e += blockDim.x) s[e] = 0.0;
+    double* s = sigma + b * (long long)kStride;
+    for (int e = threadIdx.x; e < kStride; e += blockDim.x) s[e] = 0.0;
     __syncthreads();
     for (int r = 3 + threadIdx.x; r < kN; r += blockDim.x) s[tile_at(r, r)] = kSigma0;
-    for (int e = threadIdx.x; e < kStStride; e += blockDim.x) state[b * (long long)kStStride + e] = 0.0;
     if (threadIdx.x == 0) init_flag[b] = 0;
 }
 
-// One filter's tiled Sigma -> dense row-major N x N (ld = N).
+// One filter's Sigma -> dense row-major N x N (ld = N).
 __global__ void k_fused_tile_unpack(const double* __restrict__ s, double* __restrict__ out) {
     for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < kN * kN; e += gridDim.x * blockDim.x) {
         const int r = e / kN, c = e - r * kN;
