@@ -46,6 +46,8 @@ SIGNATURES = {
     "ekf_get_state": (ctypes.c_int, [ctypes.c_void_p, c_double_p]),
     "ekf_set_state": (ctypes.c_int, [ctypes.c_void_p, c_double_p]),
     "ekf_get_sigma": (ctypes.c_int, [ctypes.c_void_p, c_double_p, ctypes.c_int64]),
+    "ekf_get_sigma_rows": (ctypes.c_int, [ctypes.c_void_p, c_i64_p, ctypes.c_int, c_double_p, ctypes.c_int64]),
+    "ekf_get_sigma_diag": (ctypes.c_int, [ctypes.c_void_p, c_double_p]),
     "ekf_set_sigma": (ctypes.c_int, [ctypes.c_void_p, c_double_p, ctypes.c_int64]),
     "ekf_get_init_flag": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_int)]),
     "ekf_set_init_flag": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
@@ -142,6 +144,8 @@ SIGNATURES_SHARDED = {
     "ekf_sharded_get_state": (ctypes.c_int, [ctypes.c_void_p, c_double_p]),
     "ekf_sharded_rows": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, c_i64_p, c_i64_p]),
     "ekf_sharded_get_sigma_rows": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, c_double_p, ctypes.c_int64]),
+    "ekf_sharded_get_sigma_row_list": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, c_i64_p, ctypes.c_int, c_double_p,
+                                                      ctypes.c_int64]),
     "ekf_sharded_update_count": (ctypes.c_int, [ctypes.c_void_p, c_u64_p]),
     "ekf_sharded_sweep_count": (ctypes.c_int, [ctypes.c_void_p, c_u64_p]),
     "ekf_sharded_set_carry_pending": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),

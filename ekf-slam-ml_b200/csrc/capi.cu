@@ -787,6 +787,35 @@ int ekf_get_sigma(ekf_filter* h, double* out, int64_t ld) {
     CU(cudaStreamSynchronize(h->stream));
     return EKF_OK;
 }
+// Selected rows of Sigma (each N doubles, row stride ld in `out`) and its diagonal: the parity checks of maps whose
+// whole covariance does not fit the host comfortably (n = 40,000: 51 GB) read these instead of ekf_get_sigma.
+int ekf_get_sigma_rows(ekf_filter* h, const int64_t* rows, int count, double* out, int64_t ld) {
+    if (!h || count < 0 || (count > 0 && (!rows || !out)) || ld < h->N) return fail(EKF_ERR_INVALID, "invalid argument");
+    for (int k = 0; k < count; ++k)
+        if (rows[k] < 0 || rows[k] >= h->N) return fail(EKF_ERR_INVALID, "row %lld out of range", (long long)rows[k]);
+    DeviceGuard g(h->device);
+    {
+        int rc_ = stream_settle(h);
+        if (rc_) return rc_;
+    }
+    for (int k = 0; k < count; ++k)
+        CU(cudaMemcpyAsync(out + (size_t)k * ld, h->d_sigma + (size_t)rows[k] * h->ld, sizeof(double) * h->N,
+                           cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return EKF_OK;
+}
+int ekf_get_sigma_diag(ekf_filter* h, double* out) {
+    if (!h || !out) return fail(EKF_ERR_INVALID, "null argument");
+    DeviceGuard g(h->device);
+    {
+        int rc_ = stream_settle(h);
+        if (rc_) return rc_;
+    }
+    CU(cudaMemcpy2DAsync(out, sizeof(double), h->d_sigma, sizeof(double) * (h->ld + 1), sizeof(double), h->N,
+                         cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return EKF_OK;
+}
 int ekf_set_sigma(ekf_filter* h, const double* in, int64_t ld) {
     if (!h || !in || ld < h->N) return fail(EKF_ERR_INVALID, "invalid argument");
     DeviceGuard g(h->device);

@@ -132,13 +132,17 @@ __device__ __forceinline__ void gather_rows(double* __restrict__ G3, double* __r
         for (int r = 0; r < 3; ++r) dst[r] = hi ? rob[r][1] : rob[r][0];
     }
     const int g = lane >> 2, t = lane & 3;
-    switch (I) {
-        case 0: gather_block_row<0>(G3, G4, C, g, t, o); break;
-        case 1: gather_block_row<1>(G3, G4, C, g, t, o); break;
-        case 2: gather_block_row<2>(G3, G4, C, g, t, o); break;
-        case 3: gather_block_row<3>(G3, G4, C, g, t, o); break;
-        default: gather_block_row<4>(G3, G4, C, g, t, o); break;
-    }
+    // compare-and-branch chain: a switch becomes a jump table, i.e. a constant load plus an indirect branch
+    if (I == 0)
+        gather_block_row<0>(G3, G4, C, g, t, o);
+    else if (I == 1)
+        gather_block_row<1>(G3, G4, C, g, t, o);
+    else if (I == 2)
+        gather_block_row<2>(G3, G4, C, g, t, o);
+    else if (I == 3)
+        gather_block_row<3>(G3, G4, C, g, t, o);
+    else
+        gather_block_row<4>(G3, G4, C, g, t, o);
 }
 
 // ---- one landmark correction (ekf_slam.cpp:138-192) around the warp's shared-memory exchanges ---------------------
@@ -259,9 +263,9 @@ __device__ __forceinline__ double rsqrt_normal_range(double d, bool& special) {
     return fma(c, ye, y);
 }
 
-static __constant__ double kAsinCoef[9] = {12155.0 / 2490368.0, 6435.0 / 557056.0, 143.0 / 10240.0,
-                                           231.0 / 13312.0,     63.0 / 2816.0,      35.0 / 1152.0,
-                                           5.0 / 112.0,         3.0 / 40.0,         1.0 / 6.0};
+// asin(x) = x + x^3 (1/6 + 3/40 x^2 + ... + 231/13312 x^10) for |x| < 1/16: the first dropped term is 6e-17 x
+static __constant__ double kAsinCoef[6] = {231.0 / 13312.0, 63.0 / 2816.0, 35.0 / 1152.0,
+                                           5.0 / 112.0,     3.0 / 40.0,    1.0 / 6.0};
 
 // same arithmetic as make_innov (ekf_math.cuh) on its fast path; `slow` is set where make_innov would leave it
 __device__ __forceinline__ Innov make_innov_nobranch(double mx, double my, double sth, double cth, double x, double y,
@@ -280,11 +284,11 @@ __device__ __forceinline__ Innov make_innov_nobranch(double mx, double my, doubl
     const double px = fma(sth, dy, cth * dx), py = fma(cth, dy, -(sth * dx));
     const double sn = fma(px, z.uy, -(py * z.ux)) * isq;
     const double cs = fma(px, z.ux, py * z.uy);
-    slow = special || !(cs > 0.0 && fabs(sn) < 0.125);
+    slow = special || !(cs > 0.0 && fabs(sn) < 0.0625);
     const double x2 = sn * sn;
     double pl = kAsinCoef[0];
 #pragma unroll
-    for (int k = 1; k < 9; ++k) pl = fma(pl, x2, kAsinCoef[k]);
+    for (int k = 1; k < 6; ++k) pl = fma(pl, x2, kAsinCoef[k]);
     h.nu1 = fma(sn * x2, pl, sn);
     return h;
 }
@@ -327,6 +331,23 @@ static __device__ __noinline__ void landmark_from_reading_cold(double sx, double
 }
 
 __device__ __forceinline__ void prefetch_l2(const void* ptr) { asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr)); }
+// Input loads as volatile asm: they stay where they are written, i.e. all of a filter's inputs are in flight together
+// instead of one L2 round trip after the other (ptxas otherwise sinks each load to its first use).
+__device__ __forceinline__ double ldg_f64_early(const double* ptr) {
+    double v;
+    asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(v) : "l"(ptr));
+    return v;
+}
+__device__ __forceinline__ int ldg_s32_early(const int32_t* ptr) {
+    int v;
+    asm volatile("ld.global.nc.s32 %0, [%1];" : "=r"(v) : "l"(ptr));
+    return v;
+}
+__device__ __forceinline__ unsigned ldg_u8_early(const uint8_t* ptr) {
+    unsigned v;
+    asm volatile("ld.global.nc.u8 %0, [%1];" : "=r"(v) : "l"(ptr));
+    return v;
+}
 
 // Persistent kernel: one warp per CTA, 148 x EKF_TILE_MINB CTAs, each walking filters b, b + grid, ...  While a filter
 // is being corrected in registers, the bulk copy engine lands the next one's Sigma and state in shared memory and its
@@ -374,26 +395,27 @@ __global__ void __launch_bounds__(32, EKF_TILE_MINB) ekf_fused_tile_kernel(const
         // before the first use
         double dtheta = 0.0, dxv = 0.0;
         if (p.mode & kDoPredict) {
-            dtheta = p.twists[2 * b];
-            dxv = p.twists[2 * b + 1];
+            dtheta = ldg_f64_early(p.twists + 2 * b);
+            dxv = ldg_f64_early(p.twists + 2 * b + 1);
         }
-        int init_flag = p.init_flag[b];
+        int init_flag = p.init_flag[b];  // plain load: written by this kernel
         int m = 0;
         unsigned vismask = 0u;
         int sp_begin = 0, sp_count = 0, sp_next = 0;
         if (!ASSOC && (p.mode & kDoMeasurement) && (p.mode & kSparseReadings)) {
             // marker list: p.mcount = CSR offsets [B + 1], p.vis = landmark ids, p.xy = (x, y) per listed marker
-            sp_begin = p.mcount[b];
-            sp_count = p.mcount[b + 1] - sp_begin;
-            if (more) sp_next = p.mcount[bn];
+            sp_begin = ldg_s32_early(p.mcount + b);
+            sp_count = ldg_s32_early(p.mcount + b + 1) - sp_begin;
+            if (more) sp_next = ldg_s32_early(p.mcount + bn);
             if (sp_begin < 0 || sp_count < 0 || (long long)sp_begin + sp_count > p.sparse_total) sp_count = 0;
             for (int k0 = 0; k0 < sp_count; k0 += 32) {
                 const int k = k0 + lane;
                 const bool on = k < sp_count;
                 int id = 0;
                 if (on) {
-                    const double sx = p.xy[2 * (long long)(sp_begin + k)], sy = p.xy[2 * (long long)(sp_begin + k) + 1];
-                    id = p.vis[sp_begin + k];
+                    const double sx = ldg_f64_early(p.xy + 2 * (long long)(sp_begin + k)),
+                                 sy = ldg_f64_early(p.xy + 2 * (long long)(sp_begin + k) + 1);
+                    id = (int)ldg_u8_early(p.vis + sp_begin + k);
                     const Reading z = make_reading(sx, sy);
                     if (id < n) {
                         zbuf[3 * id] = z.zr;
@@ -405,8 +427,8 @@ __global__ void __launch_bounds__(32, EKF_TILE_MINB) ekf_fused_tile_kernel(const
             }
         } else if (!ASSOC && (p.mode & kDoMeasurement)) {
             const int ls = lane < n ? lane : 0;
-            const double sx = p.xy[b * 2 * n + 2 * ls], sy = p.xy[b * 2 * n + 2 * ls + 1];
-            const uint8_t vb = p.vis[b * n + ls];
+            const double sx = ldg_f64_early(p.xy + b * 2 * n + 2 * ls), sy = ldg_f64_early(p.xy + b * 2 * n + 2 * ls + 1);
+            const unsigned vb = ldg_u8_early(p.vis + b * n + ls);
             vismask = __ballot_sync(kFull, lane < n && vb != 0);
             if (lane < n) {  // range and unit direction of every slot's reading (ekf_slam.cpp:140-146)
                 const Reading z = make_reading(sx, sy);
@@ -571,15 +593,18 @@ __global__ void __launch_bounds__(32, EKF_TILE_MINB) ekf_fused_tile_kernel(const
                     gain_w<true>(G3, G4, Wab + kBufStride, Kab, rob, wa, wb, lane, ib, h);
                     gain_k(Wab + kBufStride, Kab + kBufStride, st, rob, stl, wb, lane, ib, h, h.nu0, h.nu1);
                     ++n_corr;
-                    // next pair's first landmark (after the last correction the values are simply not used)
-                    ia = rem ? __ffs(rem) - 1 : ib;
+                    if (!rem) {
+                        pass_blocks<true>(C, Kab, Wab, lane);
+                        break;
+                    }
+                    // next pair's first landmark: H_j / nu in one basic block with the pass
+                    ia = __ffs(rem) - 1;
+                    rem &= rem - 1;
                     slow = false;
                     if (!(EKF_TILE_DBG & 4))
                         h = make_innov_nobranch(st[3 + 2 * ia], st[4 + 2 * ia], cst[3], cst[4], cst[1], cst[2],
                                                 Reading{zbuf[3 * ia], zbuf[3 * ia + 1], zbuf[3 * ia + 2]}, slow);
                     pass_blocks<true>(C, Kab, Wab, lane);
-                    if (!rem) break;
-                    rem &= rem - 1;
                     if (slow)
                         h = make_innov_cold(st[3 + 2 * ia], st[4 + 2 * ia], cst[0], cst[3], cst[4], cst[1], cst[2],
                                             zbuf[3 * ia], zbuf[3 * ia + 1], zbuf[3 * ia + 2]);

@@ -829,6 +829,24 @@ int ekf_sharded_get_sigma_rows(ekf_sharded* h, int shard, double* out, int64_t l
     CU(cudaStreamSynchronize(h->stream));
     return 0;
 }
+// Selected GLOBAL rows owned by shard `shard` (NCCL mode: 0 = this rank), N doubles each, row stride ld in `out`.
+int ekf_sharded_get_sigma_row_list(ekf_sharded* h, int shard, const int64_t* rows, int count, double* out, int64_t ld) {
+    if (!h || shard < 0 || shard >= (int)h->sh.size() || count < 0 || (count > 0 && (!rows || !out)) || ld < h->N)
+        return fail(-1, "invalid argument");
+    Shard& s = h->sh[shard];
+    for (int k = 0; k < count; ++k)
+        if (rows[k] < s.r0 || rows[k] >= s.r1) return fail(-1, "row %lld is not owned by this shard", (long long)rows[k]);
+    Dev g(h->device);
+    {
+        int rc_ = settle(h);
+        if (rc_) return rc_;
+    }
+    for (int k = 0; k < count; ++k)
+        CU(cudaMemcpyAsync(out + (size_t)k * ld, s.sig + (size_t)(rows[k] - s.r0) * h->ld, sizeof(double) * h->N,
+                           cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return 0;
+}
 int ekf_sharded_update_count(ekf_sharded* h, uint64_t* out) {
     if (!h || !out) return fail(-1, "null argument");
     Dev g(h->device);

@@ -203,6 +203,21 @@ class EKF_SLAM:
         assert v.shape == (self.N, self.N)
         check(self._L.ekf_set_sigma(self._h, v.ctypes.data_as(c_double_p), self.N))
 
+    def sigma_rows(self, rows):
+        """Selected rows of the covariance, shape [len(rows), N] (maps too large to read back whole)."""
+        rows = np.ascontiguousarray(rows, dtype=np.int64)
+        out = np.zeros((rows.size, self.N))
+        if rows.size:
+            check(self._L.ekf_get_sigma_rows(self._h, rows.ctypes.data_as(_lib.c_i64_p), int(rows.size),
+                                             out.ctypes.data_as(c_double_p), self.N))
+        return out
+
+    @property
+    def sigma_diag(self):
+        out = np.zeros(self.N)
+        check(self._L.ekf_get_sigma_diag(self._h, out.ctypes.data_as(c_double_p)))
+        return out
+
     @property
     def init_flag(self):
         v = ctypes.c_int()

@@ -91,6 +91,15 @@ class ShardedEKF:
             _check(self._L.ekf_sharded_get_sigma_rows(self._h, int(shard), out.ctypes.data_as(c_double_p), self.N))
         return out
 
+    def sigma_row_list(self, rows, shard=0):
+        """Selected GLOBAL rows owned by `shard` (NCCL mode: 0 = this rank), shape [len(rows), N]."""
+        rows = np.ascontiguousarray(rows, dtype=np.int64)
+        out = np.zeros((rows.size, self.N))
+        if rows.size:
+            _check(self._L.ekf_sharded_get_sigma_row_list(self._h, int(shard), rows.ctypes.data_as(_lib.c_i64_p), int(rows.size),
+                                                          out.ctypes.data_as(c_double_p), self.N))
+        return out
+
     def sigma_full_local(self):
         """Local-emulation mode only: the whole covariance, assembled from all shards."""
         assert self.local

@@ -41,6 +41,8 @@ int ekf_sharded_get_state(ekf_sharded* h, double* out /* N */);
 /* rows [row_begin, row_end) owned by shard `shard` (NCCL mode: shard must be 0 = this rank) */
 int ekf_sharded_rows(ekf_sharded* h, int shard, int64_t* row_begin, int64_t* row_end);
 int ekf_sharded_get_sigma_rows(ekf_sharded* h, int shard, double* out, int64_t ld);
+/* `count` selected GLOBAL rows, all owned by `shard` (N doubles each, row stride ld in `out`) */
+int ekf_sharded_get_sigma_row_list(ekf_sharded* h, int shard, const int64_t* rows, int count, double* out, int64_t ld);
 int ekf_sharded_update_count(ekf_sharded* h, uint64_t* out);
 /* As ekf_set_carry_pending / ekf_sweep_count of ekf_slam_b200.h: correction factors stay pending across prediction()
  * and measurement() calls by default (every rank must use the same setting); verbs that read Sigma settle them. */

@@ -86,6 +86,10 @@ int ekf_get_landmarks(ekf_filter* h, double* out);
 int ekf_get_state(ekf_filter* h, double* out);
 int ekf_set_state(ekf_filter* h, const double* in);
 int ekf_get_sigma(ekf_filter* h, double* out, int64_t ld);
+/* `count` selected rows (N doubles each, row stride ld in `out`) and the diagonal (N doubles): for parity checks of
+ * maps whose whole covariance is too large to pull to the host */
+int ekf_get_sigma_rows(ekf_filter* h, const int64_t* rows, int count, double* out, int64_t ld);
+int ekf_get_sigma_diag(ekf_filter* h, double* out);
 int ekf_set_sigma(ekf_filter* h, const double* in, int64_t ld);
 int ekf_get_init_flag(ekf_filter* h, int* out);  /* landmark_init_flag, ekf_slam.cpp:50 */
 int ekf_set_init_flag(ekf_filter* h, int v);
