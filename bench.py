@@ -167,6 +167,126 @@ def run_reference_arm(args):
     print(json.dumps(line), flush=True)
 
 
+
+# ----------------------------------------------------------------------------- parity at the benchmarked sizes
+PARITY_TOL = 1e-9  # scaled metric of tests/_oracle.py (state: max|d|/max(1,|x|); covariance: |d_ab| / max(|S_ab|, sqrt(S_aa S_bb)))
+
+
+def scaled_rows_err(a, b, diag_b, row_ids, chunk=256):
+    """Scaled covariance error over selected rows: a, b [k, N] (b = the checker), diag_b [N], row_ids [k]."""
+    d = np.sqrt(np.abs(diag_b))
+    worst = 0.0
+    for i0 in range(0, a.shape[0], chunk):
+        i1 = min(i0 + chunk, a.shape[0])
+        scale = np.maximum(np.abs(b[i0:i1]), d[np.asarray(row_ids[i0:i1])][:, None] * d[None, :])
+        np.maximum(scale, 1e-300, out=scale)
+        worst = max(worst, float(np.max(np.abs(a[i0:i1] - b[i0:i1]) / scale)))
+    return worst
+
+
+def parity_cfg3(bt, tr, n, picks=64, seed=5):
+    """After the timed steps: `picks` random filters of the batch against the plain-C oracle driven through the
+    whole trajectory the batch went through (known association)."""
+    import _oracle
+    B = tr["twists"].shape[1]
+    T = tr["twists"].shape[0]
+    rng = np.random.default_rng(seed)
+    ids = sorted(set([0, B - 1] + [int(v) for v in rng.integers(0, B, picks)]))
+    states = bt.states()
+    worst_s = worst_c = 0.0
+    for b in ids:
+        o = _oracle.OracleEKF(n)
+        for t in range(T):
+            o.prediction(*tr["twists"][t, b])
+            o.measurement(tr["xy"][t, b], tr["vis"][t, b])
+        worst_s = max(worst_s, _oracle.state_err(states[b], o.state))
+        worst_c = max(worst_c, _oracle.sigma_err(bt.sigma(b), o.sigma))
+    ok = bool(worst_s < PARITY_TOL and worst_c < PARITY_TOL)
+    return {"ok": ok, "filters_checked": len(ids), "steps": int(T), "state_err": worst_s, "sigma_err": worst_c,
+            "tol": PARITY_TOL, "checker": "oracle/ekf_oracle.c (plain-C restatement pinned to the reference build)"}
+
+
+def parity_large_map(pkg, device, n_lm, tr, min_corrections=10):
+    """cfg4 size: a fresh streamed filter and the O(N^2) oracle through the init-only call and as many steps as it
+    takes to pile up >= min_corrections corrections (they stay pending on the GPU and go through ONE multi-factor
+    sweep when Sigma is read); state and the FULL covariance compared.  Also times the oracle (CPU baseline)."""
+    import _oracle
+    f = pkg.EKF_SLAM(n_lm, device=device)
+    o = _oracle.OracleEKF(n_lm)
+    N = 3 + 2 * n_lm
+    done, t, cpu_s, cpu_n = 0, 0, 0.0, 0
+    while done < min_corrections and t < tr["twists"].shape[0]:
+        f.prediction(tuple(tr["twists"][t, 0]))
+        f.measurement(tr["xy"][t, 0], tr["vis"][t, 0])
+        o.prediction(*tr["twists"][t, 0])
+        t0 = time.perf_counter()
+        o.measurement(tr["xy"][t, 0], tr["vis"][t, 0])
+        if t > 0:  # step 0 is the init-only call
+            k = int(tr["vis"][t, 0].sum())
+            cpu_s += time.perf_counter() - t0
+            cpu_n += k
+            done += k
+        t += 1
+    s0 = f.sweep_count
+    st_err = _oracle.state_err(f.state, o.state)
+    sig = f.sigma            # settles the pending factors: one sweep with P = pending corrections
+    sweeps = f.sweep_count - s0
+    ref = o.sigma
+    c_err = scaled_rows_err(sig, ref, np.diag(ref).copy(), np.arange(N), chunk=128)
+    f.close()
+    ok = bool(st_err < PARITY_TOL and c_err < PARITY_TOL)
+    par = {"ok": ok, "n_landmarks": n_lm, "state_dim": N, "corrections": done, "sweeps_at_readback": int(sweeps),
+           "state_err": st_err, "sigma_err": c_err, "tol": PARITY_TOL, "entries_compared": int(N) * int(N),
+           "checker": "oracle/ekf_oracle.c, O(N^2) form"}
+    cpu = {"value": cpu_n / cpu_s if cpu_s > 0 else None, "unit": UNIT, "cores": 1, "kind": "port",
+           "sample": f"{cpu_n} corrections at N={N}, plain-C O(N^2) port (the dense reference needs 2N^3 = "
+                     f"{2.0 * N ** 3 / 1e12:.1f} TFLOP per correction and is intractable)"}
+    return par, cpu
+
+
+def parity_sharded(pkg, dist, local, n_lm, tr, min_corrections=10, sample_rows=None, seed=11):
+    """cfg5: the row-sharded filter over the real NCCL ranks against the single-GPU streamed engine (one replica per
+    rank, same inputs).  sample_rows = None: every owned row (full covariance); else that many rows in total."""
+    from ekf_slam_ml_b200.sharded import ShardedEKF
+    world, rank = dist.get_world_size(), dist.get_rank()
+    f = ShardedEKF.from_process_group(n_lm, dist, local)
+    g = pkg.EKF_SLAM(n_lm, device=local, engine=pkg.ENGINE_STREAM)
+    N = 3 + 2 * n_lm
+    done, t = 0, 0
+    while done < min_corrections and t < tr["twists"].shape[0]:
+        for obj in (f, g):
+            obj.prediction(tuple(tr["twists"][t, 0]))
+            obj.measurement(tr["xy"][t, 0], tr["vis"][t, 0])
+        if t > 0:
+            done += int(tr["vis"][t, 0].sum())
+        t += 1
+    st_err = float(np.max(np.abs(f.state - g.state) / np.maximum(1.0, np.abs(g.state))))
+    r0, r1 = f.rows(0)
+    if sample_rows is None:
+        rows = np.arange(r0, r1, dtype=np.int64)
+    else:
+        rng = np.random.default_rng(seed + rank)
+        k = max(1, sample_rows // world)
+        rows = np.unique(np.concatenate([[r0, r1 - 1], rng.integers(r0, r1, k)])).astype(np.int64)
+    diag = g.sigma_diag
+    worst = 0.0
+    for i0 in range(0, rows.size, 128):
+        part = rows[i0:i0 + 128]
+        worst = max(worst, scaled_rows_err(f.sigma_row_list(part), g.sigma_rows(part), diag, part))
+    f.close()
+    g.close()
+    import torch
+    e = torch.tensor([st_err, worst], dtype=torch.float64, device="cuda")
+    cnt = torch.tensor([float(rows.size)], dtype=torch.float64, device="cuda")
+    dist.all_reduce(e, op=dist.ReduceOp.MAX)
+    dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+    st_err, worst = float(e[0].item()), float(e[1].item())
+    return {"ok": bool(st_err < PARITY_TOL and worst < PARITY_TOL), "n_landmarks": n_lm, "state_dim": N,
+            "corrections": done, "rows_compared": int(cnt.item()), "state_err": st_err, "sigma_err": worst,
+            "tol": PARITY_TOL, "nccl_ranks": world,
+            "checker": "single-GPU streamed engine (itself checked against the oracle at n = 8,192 in large_map.parity)"}
+
+
 # ----------------------------------------------------------------------------- our arm
 def large_map_leg(pkg, device, n_lm, timed_updates, peak_gbs, want_cpu):
     """cfg4: one filter, n_lm landmarks; streamed gain + sweep per correction."""
@@ -220,20 +340,12 @@ def large_map_leg(pkg, device, n_lm, timed_updates, peak_gbs, want_cpu):
                      "note": "one launch moves Sigma once (16 N^2 B) and applies up to 14 pending corrections; per_update_* "
                              "is SURVEY.md's 16 N^2-per-correction convention and exceeds 1 for that reason"},
     }
-    if want_cpu:
-        import _oracle
-        o = _oracle.OracleEKF(n_lm)
-        o.prediction(*tr["twists"][0, 0])
-        o.measurement(tr["xy"][0, 0], tr["vis"][0, 0])
-        vis = np.zeros(n_lm, np.uint8)
-        vis[np.flatnonzero(tr["vis"][5, 0])[:3]] = 1
-        t0 = time.perf_counter()
-        o.measurement(tr["xy"][5, 0], vis)
-        sec = time.perf_counter() - t0
-        out["cpu_baseline"] = {"value": float(vis.sum()) / sec, "unit": UNIT, "cores": 1, "kind": "port",
-                               "sample": f"{int(vis.sum())} corrections at N={N}, plain-C O(N^2) port (the dense reference "
-                                         f"needs 2N^3 = {2.0 * N ** 3 / 1e12:.1f} TFLOP per correction and is intractable)"}
     f.close()
+    # untimed: parity at this size through the multi-factor sweep, against the O(N^2) oracle (which is the CPU baseline)
+    par, cpu = parity_large_map(pkg, device, n_lm, tr)
+    out["parity"] = par
+    if want_cpu:
+        out["cpu_baseline"] = cpu
     return out
 
 
@@ -248,6 +360,12 @@ def sharded_map_leg(pkg, dist, local, n_lm, timed_updates, peak_gbs):
     w = tg.grid_world(nx, nx, pitch=0.5, n_slots=n_lm, max_visible=0.7)
     steps = 40
     tr = tg.simulate_known(w, 1, steps, seed=77)
+    # untimed: parity over the real NCCL ranks, full covariance at the cfg4 size and sampled rows at this size
+    n_small = 8192
+    w_small = tg.grid_world(128, 64, pitch=0.5, n_slots=n_small, max_visible=0.7)
+    par_small = parity_sharded(pkg, dist, local, n_small, tg.simulate_known(w_small, 1, 8, seed=99))
+    par_full = parity_sharded(pkg, dist, local, n_lm, tr, sample_rows=1000)
+    dist.barrier()
     f = ShardedEKF.from_process_group(n_lm, dist, local)
     N = 3 + 2 * n_lm
     t = 0
@@ -283,6 +401,8 @@ def sharded_map_leg(pkg, dist, local, n_lm, timed_updates, peak_gbs):
                      "updates_per_sweep": done / max(n_sweeps, 1),
                      "per_update_achieved": per_gpu_bytes / (ms_upd * 1e-3) / 1e9,
                      "per_update_frac": per_gpu_bytes / (ms_upd * 1e-3) / 1e9 / peak_gbs},
+        "parity": {"ok": bool(par_small["ok"] and par_full["ok"]), "nccl_ranks": world,
+                   "n8192_full_sigma": par_small, f"n{n_lm}_sampled_rows": par_full},
     }
     f.close()
     return out
@@ -532,6 +652,14 @@ def run_ours(args):
     h2d = B * 2 * 8 + (B + 1) * 4 + float(np.mean(totals[W:T])) * 17
     d2h = B * 3 * 8
 
+    # ---- untimed: parity of this rank's batch at the benchmarked size (64 random filters, whole trajectory)
+    par3 = parity_cfg3(bt, tr, n)
+    if dist:
+        flag = torch.tensor([0.0 if par3["ok"] else 1.0, par3["state_err"], par3["sigma_err"]], dtype=torch.float64, device="cuda")
+        dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+        par3.update(ok=bool(flag[0].item() == 0.0), state_err=float(flag[1].item()), sigma_err=float(flag[2].item()),
+                    ranks=world)
+
     # ---- error statistics: the only inter-rank exchange of this workload (NCCL all-reduce of 4 doubles)
     err = bt.pose_error(np.ascontiguousarray(tr["truth"][3 * T][:, [0, 1, 2]]))
     e_t = torch.tensor(err, dtype=torch.float64, device="cuda")
@@ -606,11 +734,23 @@ def run_ours(args):
         torch.cuda.empty_cache()
         sm = sharded_map_leg(pkg, dist, local, args.sharded_n, args.sharded_updates, peak_gbs)
         line["sharded_map"] = sm
+    # parity summary: every leg that ran carries its own check; a mismatch makes the run fail (rc != 0)
+    parity = {"cfg3": par3}
+    if "large_map" in line:
+        parity["cfg4"] = line["large_map"]["parity"]
+    if "sharded_map" in line:
+        parity["cfg5"] = line["sharded_map"]["parity"]
+        parity["nccl_ranks"] = world
+    parity["ok"] = bool(all(v["ok"] for k, v in parity.items() if isinstance(v, dict)))
+    line["parity"] = parity
     if rank == 0:
         print(json.dumps(line), flush=True)
     if dist:
         dist.barrier()
         dist.destroy_process_group()
+    if not parity["ok"]:
+        sys.stderr.write("bench.py: PARITY MISMATCH at a benchmarked size: %s\n" % json.dumps(parity))
+        sys.exit(3)
 
 
 def main():

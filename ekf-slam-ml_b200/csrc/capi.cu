@@ -1414,6 +1414,18 @@ int ekf_batch_timer_stop(ekf_batch* b, float* ms_out) {
     *ms_out = best;
     return EKF_OK;
 }
+#if EKF_TILE_PROF
+// development builds only: per-phase clock totals of the tile kernel since the last call (then reset)
+int ekf_debug_tile_prof(uint64_t* out16) {
+    unsigned long long v[16];
+    CU(cudaDeviceSynchronize());
+    CU(cudaMemcpyFromSymbol(v, tile::g_tile_prof, sizeof(v)));
+    for (int k = 0; k < 16; ++k) out16[k] = v[k];
+    unsigned long long z[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    CU(cudaMemcpyToSymbol(tile::g_tile_prof, z, sizeof(z)));
+    return EKF_OK;
+}
+#endif
 int ekf_batch_launch_count(ekf_batch* b, uint64_t* out) {
     if (!b || !out) return fail(EKF_ERR_INVALID, "null argument");
     *out = b->launches;

@@ -40,8 +40,26 @@
 #define EKF_TILE_MINB 12  // resident filters per SM the kernel is compiled for
 #endif
 
+#ifndef EKF_TILE_PROF
+#define EKF_TILE_PROF 0  // 1: per-phase clock64() totals in g_tile_prof (development builds only)
+#endif
+
 namespace ekf {
 namespace tile {
+
+#if EKF_TILE_PROF
+__device__ unsigned long long g_tile_prof[16];
+#define TILE_PROF_MARK(k)                                 \
+    do {                                                  \
+        const long long now_ = clock64();                 \
+        prof_acc[k] += (unsigned long long)(now_ - prof_t); \
+        prof_t = now_;                                    \
+    } while (0)
+#else
+#define TILE_PROF_MARK(k) \
+    do {                  \
+    } while (0)
+#endif
 
 constexpr int kNL = 20, kN = 43;
 constexpr int kBS = 8;                        // block edge: four landmarks
@@ -79,8 +97,8 @@ struct TileSmem {
         int o = 0;
         off_land = o, o += kStride * 8;       // landing buffer of the NEXT filter (bulk copy), 9,088 B
         off_bar = o, o += 16;                 // mbarrier of that copy
-        off_g = o, o += 2 * kGStride * 8;     // rows 3+2i / 4+2i of the correction (index c at [c + 1]: column 3 is
-                                              // 16-B aligned for the two-column stores of the gather)
+        off_g = o, o += 4 * kGStride * 8;     // rows 3+2i / 4+2i of a pair's two corrections (index c at [c + 1]:
+                                              // column 3 is 16-B aligned for the two-column stores of the gather)
         off_w = o, o += 2 * kBufStride * 16;  // W = H_j Sigma, one pair per column; first / second correction of a pair
         off_k = o, o += 2 * kBufStride * 16;  // K, one pair per row; likewise
         off_st = o, o += kPad * 8;            // mirror of the state (landmark positions for the next H_j)
@@ -117,13 +135,11 @@ __device__ __forceinline__ void gather_block_row(double* __restrict__ G3, double
     }
 }
 
-__device__ __forceinline__ void gather_rows(double* __restrict__ G3, double* __restrict__ G4,
-                                            const double (&C)[kBlocks][2], const double (&rob)[3][2], const int lane,
-                                            const int i) {
+// columns 0..2 of the two rows: the mirror of the robot rows at columns 3+2i, 4+2i (always up to date)
+__device__ __forceinline__ void gather_robot_cols(double* __restrict__ G3, double* __restrict__ G4,
+                                                  const double (&rob)[3][2], const int lane, const int i) {
     if (EKF_TILE_DBG & 2) return;
-    const int I = i >> 2, o = i & 3;  // warp-uniform
     const int i3 = 3 + 2 * i, i4 = i3 + 1;
-    // columns 0..2 of the two rows are the mirror of the robot rows at columns i3, i4
     const bool m3 = lane == (i3 & 31), m4 = lane == (i4 & 31);
     if (m3 || m4) {
         const bool hi = (m3 ? i3 : i4) >= 32;
@@ -131,6 +147,12 @@ __device__ __forceinline__ void gather_rows(double* __restrict__ G3, double* __r
 #pragma unroll
         for (int r = 0; r < 3; ++r) dst[r] = hi ? rob[r][1] : rob[r][0];
     }
+}
+// columns 3.. of the two rows, from the landmark blocks
+__device__ __forceinline__ void gather_blocks(double* __restrict__ G3, double* __restrict__ G4,
+                                              const double (&C)[kBlocks][2], const int lane, const int i) {
+    if (EKF_TILE_DBG & 2) return;
+    const int I = i >> 2, o = i & 3;  // warp-uniform
     const int g = lane >> 2, t = lane & 3;
     // compare-and-branch chain: a switch becomes a jump table, i.e. a constant load plus an indirect branch
     if (I == 0)
@@ -143,6 +165,12 @@ __device__ __forceinline__ void gather_rows(double* __restrict__ G3, double* __r
         gather_block_row<3>(G3, G4, C, g, t, o);
     else
         gather_block_row<4>(G3, G4, C, g, t, o);
+}
+__device__ __forceinline__ void gather_rows(double* __restrict__ G3, double* __restrict__ G4,
+                                            const double (&C)[kBlocks][2], const double (&rob)[3][2], const int lane,
+                                            const int i) {
+    gather_robot_cols(G3, G4, rob, lane, i);
+    gather_blocks(G3, G4, C, lane, i);
 }
 
 // ---- one landmark correction (ekf_slam.cpp:138-192) around the warp's shared-memory exchanges ---------------------
@@ -331,21 +359,21 @@ static __device__ __noinline__ void landmark_from_reading_cold(double sx, double
 }
 
 __device__ __forceinline__ void prefetch_l2(const void* ptr) { asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr)); }
-// Input loads as volatile asm: they stay where they are written, i.e. all of a filter's inputs are in flight together
-// instead of one L2 round trip after the other (ptxas otherwise sinks each load to its first use).
+// Input loads with the PTX .volatile qualifier: ptxas may neither sink them to their first use nor predicate them
+// away, so all of a filter's inputs are in flight together instead of one L2 round trip after the other.
 __device__ __forceinline__ double ldg_f64_early(const double* ptr) {
     double v;
-    asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(v) : "l"(ptr));
+    asm volatile("ld.volatile.global.f64 %0, [%1];" : "=d"(v) : "l"(ptr));
     return v;
 }
 __device__ __forceinline__ int ldg_s32_early(const int32_t* ptr) {
     int v;
-    asm volatile("ld.global.nc.s32 %0, [%1];" : "=r"(v) : "l"(ptr));
+    asm volatile("ld.volatile.global.s32 %0, [%1];" : "=r"(v) : "l"(ptr));
     return v;
 }
 __device__ __forceinline__ unsigned ldg_u8_early(const uint8_t* ptr) {
     unsigned v;
-    asm volatile("ld.global.nc.u8 %0, [%1];" : "=r"(v) : "l"(ptr));
+    asm volatile("ld.volatile.global.u8 %0, [%1];" : "=r"(v) : "l"(ptr));
     return v;
 }
 
@@ -360,6 +388,7 @@ __global__ void __launch_bounds__(32, EKF_TILE_MINB) ekf_fused_tile_kernel(const
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + S.off_bar);
     double* G3 = reinterpret_cast<double*>(smem_raw + S.off_g) + 1;
     double* G4 = G3 + kGStride;
+    double *G3b = G3 + 2 * kGStride, *G4b = G3b + kGStride;  // second correction of a pair
     double2* Wab = reinterpret_cast<double2*>(smem_raw + S.off_w);
     double2* Kab = reinterpret_cast<double2*>(smem_raw + S.off_k);
     double* st = reinterpret_cast<double*>(smem_raw + S.off_st);
@@ -384,12 +413,18 @@ __global__ void __launch_bounds__(32, EKF_TILE_MINB) ekf_fused_tile_kernel(const
     }
     // padded tails of the per-column arrays stay zero for the whole launch
     G3[lane] = G3[lane + 32] = G4[lane] = G4[lane + 32] = 0.0;
+    G3b[lane] = G3b[lane + 32] = G4b[lane] = G4b[lane + 32] = 0.0;
     uint32_t phase = 0;
     int n_corr = 0;
+#if EKF_TILE_PROF
+    unsigned long long prof_acc[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    long long prof_t = clock64();
+#endif
 
     for (; b < p.B; b += stride_b) {
         const long long bn = b + stride_b;
         const bool more = bn < p.B;
+        TILE_PROF_MARK(7);
 
         // ---- this filter's inputs (in L2 already, thanks to the previous iteration's prefetch); every load is issued
         // before the first use
@@ -448,8 +483,10 @@ __global__ void __launch_bounds__(32, EKF_TILE_MINB) ekf_fused_tile_kernel(const
             }
         }
 
+        TILE_PROF_MARK(0);  // inputs issued / reduced
         // ---- this filter's Sigma and state: landing buffer -> registers (lane-major, conflict-free)
         mbar_wait(bar, phase);
+        TILE_PROF_MARK(1);  // wait for the landing buffer
         phase ^= 1u;
         double C[kBlocks][2], rob[3][2], stl[2];
 #pragma unroll
@@ -521,6 +558,7 @@ __global__ void __launch_bounds__(32, EKF_TILE_MINB) ekf_fused_tile_kernel(const
         st[lane] = stl[0];
         st[lane + 32] = stl[1];
         __syncwarp();
+        TILE_PROF_MARK(2);  // landing buffer -> registers, prediction
 
         double2 wa[2], wb[2];  // this lane's W pairs of the pair's first / second correction
 
@@ -569,20 +607,27 @@ __global__ void __launch_bounds__(32, EKF_TILE_MINB) ekf_fused_tile_kernel(const
                 // chain and the tensor pipe overlap.
                 int ia = __ffs(rem) - 1;
                 rem &= rem - 1;
+                int ib = rem ? __ffs(rem) - 1 : -1;  // the pair's second landmark, if any
                 Innov h = make_innov(st[3 + 2 * ia], st[4 + 2 * ia], theta, sth, cth, x, y,
                                      Reading{zbuf[3 * ia], zbuf[3 * ia + 1], zbuf[3 * ia + 2]});
+                // both landmarks' rows come from the same landmark blocks (no pass in between); only the robot
+                // columns of the second one's rows wait for the first correction
                 gather_rows(G3, G4, C, rob, lane, ia);
+                if (ib >= 0) gather_blocks(G3b, G4b, C, lane, ib);
+                TILE_PROF_MARK(3);  // measurement() entry: init check, first H_j, first gather
                 for (;;) {
                     gain_w<false>(G3, G4, Wab, nullptr, rob, wa, wa, lane, ia, h);
+                    TILE_PROF_MARK(8);
                     gain_k(Wab, Kab, st, rob, stl, wa, lane, ia, h, h.nu0, h.nu1);
+                    TILE_PROF_MARK(9);
                     ++n_corr;
-                    if (!rem) {  // odd count: the last correction goes through alone
+                    if (ib < 0) {  // odd count: the last correction goes through alone
                         pass_blocks<false>(C, Kab, Wab, lane);
+                        TILE_PROF_MARK(13);
                         break;
                     }
-                    const int ib = __ffs(rem) - 1;
                     rem &= rem - 1;
-                    gather_rows(G3, G4, C, rob, lane, ib);  // rows of the blocks that still lack the first factor
+                    gather_robot_cols(G3b, G4b, rob, lane, ib);
                     bool slow = false;
                     if (!(EKF_TILE_DBG & 4))
                         h = make_innov_nobranch(st[3 + 2 * ib], st[4 + 2 * ib], cst[3], cst[4], cst[1], cst[2],
@@ -590,16 +635,21 @@ __global__ void __launch_bounds__(32, EKF_TILE_MINB) ekf_fused_tile_kernel(const
                     if (slow)
                         h = make_innov_cold(st[3 + 2 * ib], st[4 + 2 * ib], cst[0], cst[3], cst[4], cst[1], cst[2],
                                             zbuf[3 * ib], zbuf[3 * ib + 1], zbuf[3 * ib + 2]);
-                    gain_w<true>(G3, G4, Wab + kBufStride, Kab, rob, wa, wb, lane, ib, h);
+                    TILE_PROF_MARK(10);
+                    gain_w<true>(G3b, G4b, Wab + kBufStride, Kab, rob, wa, wb, lane, ib, h);
+                    TILE_PROF_MARK(11);
                     gain_k(Wab + kBufStride, Kab + kBufStride, st, rob, stl, wb, lane, ib, h, h.nu0, h.nu1);
+                    TILE_PROF_MARK(12);
                     ++n_corr;
                     if (!rem) {
                         pass_blocks<true>(C, Kab, Wab, lane);
+                        TILE_PROF_MARK(13);
                         break;
                     }
                     // next pair's first landmark: H_j / nu in one basic block with the pass
                     ia = __ffs(rem) - 1;
                     rem &= rem - 1;
+                    ib = rem ? __ffs(rem) - 1 : -1;
                     slow = false;
                     if (!(EKF_TILE_DBG & 4))
                         h = make_innov_nobranch(st[3 + 2 * ia], st[4 + 2 * ia], cst[3], cst[4], cst[1], cst[2],
@@ -608,8 +658,11 @@ __global__ void __launch_bounds__(32, EKF_TILE_MINB) ekf_fused_tile_kernel(const
                     if (slow)
                         h = make_innov_cold(st[3 + 2 * ia], st[4 + 2 * ia], cst[0], cst[3], cst[4], cst[1], cst[2],
                                             zbuf[3 * ia], zbuf[3 * ia + 1], zbuf[3 * ia + 2]);
+                    TILE_PROF_MARK(14);
                     if (!staged_next) stage_next();  // every register loaded from the landing buffer has been used
                     gather_rows(G3, G4, C, rob, lane, ia);
+                    if (ib >= 0) gather_blocks(G3b, G4b, C, lane, ib);
+                    TILE_PROF_MARK(15);
                 }
                 if (!staged_next) stage_next();
             }
@@ -735,6 +788,7 @@ __global__ void __launch_bounds__(32, EKF_TILE_MINB) ekf_fused_tile_kernel(const
             }
         }
 
+        TILE_PROF_MARK(4);  // corrections
         // ---- write back: registers -> HBM, same lane-major order
         double* go = p.sigma + b * (long long)kStride;
 #pragma unroll
@@ -751,7 +805,12 @@ __global__ void __launch_bounds__(32, EKF_TILE_MINB) ekf_fused_tile_kernel(const
         if (lane < kN - 32) __stcs(go + kStOff + 32 + lane, stl[1]);
         if (lane == 0) p.init_flag[b] = init_flag;
         if (!staged_next) stage_next();
+        TILE_PROF_MARK(5);  // write-back
     }
+#if EKF_TILE_PROF
+    if (lane == 0)
+        for (int k = 0; k < 16; ++k) atomicAdd(&g_tile_prof[k], prof_acc[k]);
+#endif
     if (lane == 0 && p.n_updates && n_corr) atomicAdd(p.n_updates, (unsigned long long)n_corr);
 }
 

@@ -62,11 +62,24 @@ def main():
             step(t)
         bt.sync()
         u0 = bt.update_count
+        L = pkg._lib.load()
+        prof = hasattr(L, "ekf_debug_tile_prof") if os.environ.get("EKF_B200_LIB") else False
+        if prof:
+            import ctypes
+            buf = (ctypes.c_uint64 * 16)()
+            L.ekf_debug_tile_prof(buf)
         bt.timer_start()
         for t in range(T0 + a.warmup, T0 + T):
             step(t)
         ms = bt.timer_stop()
         upd = bt.update_count - u0
+        if prof:
+            L.ekf_debug_tile_prof(buf)
+            tot = float(sum(buf))
+            names = ["inputs", "wait landing", "regs+predict", "meas entry", "corr (rest)", "write-back", "-", "loop top",
+                     "gain_w A", "gain_k A", "robcols+H_j B", "gain_w B", "gain_k B", "last pass", "H_j A' || pass", "stage+gather"]
+            print("   phase cycles per filter-step: " + ", ".join(
+                f"{n_} {buf[k] / (a.steps * B):.0f} ({100 * buf[k] / tot:.0f}%)" for k, n_ in enumerate(names) if buf[k]))
         print(f"rep {rep}: {ms / a.steps:.4f} ms/step, {upd / a.steps / B:.2f} upd/filter-step, "
               f"{upd / (ms * 1e-3):.4e} upd/s", flush=True)
         best = ms if best is None else min(best, ms)
