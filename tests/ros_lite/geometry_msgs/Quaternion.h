@@ -1,0 +1,2 @@
+#pragma once
+#include "geometry_msgs/Point.h"
