@@ -440,6 +440,177 @@ def laser_leg(pkg, device, n_scans=8192):
             "circles_per_scan": float(counts.mean()), "kernel": "k_circles_scan<float>", "gpu_launches": reps}
 
 
+
+def single_filter_leg(pkg, device, steps=400):
+    """cfg1 / cfg2: ONE reference-sized filter (n = 20) at the node's cadence: prediction + measurement() (or
+    data_association()) + pose read-back per step, through the C ABI (ctypes) and through the C++ facade, next to the
+    reference's own class on one host core.  This is a LATENCY measurement (one launch sequence per call and a
+    synchronising getter); the GPU is not expected to beat an 11 us CPU update here."""
+    import subprocess
+    import _oracle
+    tg = pkg.tracegen
+    tr = tg.simulate_known(tg.default_world(N_SLOTS), 1, steps + 21, seed=5)
+    tu = tg.simulate_unknown(tg.default_world(N_SLOTS), 1, steps + 21, seed=5)
+    out = {"workload": "cfg1 / cfg2: single filter, n = 20, default 10-tube world, one SLAM step per call sequence"}
+
+    def run(obj, known, is_ref):
+        kn = np.zeros(N_SLOTS, np.uint8)
+        lat, upd = [], 0
+        for t in range(steps + 21):
+            t0 = time.perf_counter()
+            if is_ref:
+                obj.prediction(*(tr if known else tu)["twists"][t, 0])
+            else:
+                obj.prediction(tuple((tr if known else tu)["twists"][t, 0]))
+            if known:
+                obj.measurement(tr["xy"][t, 0], tr["vis"][t, 0])
+                k = int(tr["vis"][t, 0].sum())
+            else:
+                k = int(tu["count"][t, 0])
+                if k:
+                    obj.data_association(tu["meas"][t, 0, :k], kn)
+            _ = obj.state[:3] if is_ref else obj._pose()
+            if t > 20:
+                lat.append(time.perf_counter() - t0)
+                upd += k
+        lat = np.array(lat)
+        return {"us_per_step_mean": float(lat.mean() * 1e6), "us_per_step_median": float(np.median(lat) * 1e6),
+                "updates_per_s": upd / float(lat.sum()), "updates_per_step": upd / len(lat)}
+
+    for known in (True, False):
+        f = pkg.EKF_SLAM(N_SLOTS, device=device)
+        key = "known" if known else "unknown"
+        out[key + "_c_abi"] = run(f, known, False)
+        f.close()
+        try:
+            out[key + "_reference_cpu_1core"] = run(_oracle.RefEKF(N_SLOTS), known, True)
+        except Exception as e:  # no reference build on this box
+            out[key + "_reference_cpu_1core"] = {"unavailable": repr(e)}
+    exe = os.path.join(ROOT, "tests", "cpp", "facade_latency")
+    cmd = ["g++", "-std=c++17", "-O2", "-I" + os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "cpp", "facade_latency.cpp"),
+           "-o", exe, "-L" + os.path.join(ROOT, "ekf-slam-ml_b200"), "-lekfslam_b200", "-Wl,-rpath," + os.path.join(ROOT, "ekf-slam-ml_b200")]
+    try:
+        subprocess.run(cmd, check=True, capture_output=True, timeout=300)
+        r = subprocess.run([exe, str(steps)], check=True, capture_output=True, text=True, timeout=300)
+        out["cpp_facade"] = json.loads(r.stdout.strip().splitlines()[-1])
+    except Exception as e:
+        out["cpp_facade"] = {"unavailable": repr(e)[:300]}
+    return out
+
+
+def large_map_unknown_leg(pkg, device, n_lm, peak_gbs, steps=24):
+    """cfg4 'plus unknown association': the streamed engine's data_association() at n = 8,192 - per measurement one
+    k_large_assoc launch over the known landmarks, then (if gated in) gain + ONE single-factor sweep, because the next
+    measurement's distances need the corrected Sigma (ekf_slam.cpp:291-391)."""
+    tg = pkg.tracegen
+    nx = int(round(np.sqrt(2 * n_lm)))
+    w = tg.grid_world(nx, n_lm // nx, pitch=0.5, n_slots=n_lm, max_visible=0.7)
+    tr = tg.simulate_known(w, 1, steps + 4, seed=99)
+    import _oracle
+    f = pkg.EKF_SLAM(n_lm, device=device)
+    N = 3 + 2 * n_lm
+    # the map is built by the first measurement() call (all landmarks initialised, as in cfg4), then every step
+    # associates the visible readings WITHOUT their labels against all n_lm known landmarks.  The first two such
+    # steps run in lockstep with the oracle (untimed): association indices must be identical, state within tolerance.
+    o = _oracle.OracleEKF(n_lm)
+    f.prediction(tuple(tr["twists"][0, 0]))
+    f.measurement(tr["xy"][0, 0], tr["vis"][0, 0])
+    o.prediction(*tr["twists"][0, 0])
+    o.measurement(tr["xy"][0, 0], tr["vis"][0, 0])
+    known = np.ones(n_lm, np.uint8)
+    known_o = np.ones(n_lm, np.uint8)
+    meas_n = upd_n = 0
+    ms_total = 0.0
+    par_meas, par_same, par_margin = 0, True, np.inf
+    for t in range(1, steps + 4):
+        ids = np.flatnonzero(tr["vis"][t, 0])
+        xy = tr["xy"][t, 0].reshape(-1, 2)[ids]
+        f.prediction(tuple(tr["twists"][t, 0]))
+        if t >= 4:
+            f.sync()
+            u0 = f.update_count
+            f.timer_start()
+        r = f.data_association(xy, known) if len(ids) else None
+        if t >= 4:
+            ms_total += f.timer_stop()
+            meas_n += len(ids)
+            upd_n += f.update_count - u0
+        elif t <= 2:
+            o.prediction(*tr["twists"][t, 0])
+            if r is None:
+                continue
+            a, dmin, sec, _ = o.data_association(xy, known_o)
+            par_meas += len(ids)
+            par_same = par_same and bool(np.array_equal(r["assoc"], a))
+            has = dmin < 10.0
+            par_margin = min(par_margin, float(np.min(np.where(
+                has, np.minimum.reduce([np.abs(dmin - 10.0), np.abs(dmin - 1.0), np.abs(sec - dmin)]), np.abs(sec - 10.0)))))
+    st_err = None
+    if par_meas:
+        # the oracle stopped after step 2; compare against a second GPU filter stopped at the same point
+        g = pkg.EKF_SLAM(n_lm, device=device)
+        kg = np.ones(n_lm, np.uint8)
+        for t in range(0, 3):
+            g.prediction(tuple(tr["twists"][t, 0]))
+            if t == 0:
+                g.measurement(tr["xy"][0, 0], tr["vis"][0, 0])
+            else:
+                ids = np.flatnonzero(tr["vis"][t, 0])
+                if len(ids):
+                    g.data_association(tr["xy"][t, 0].reshape(-1, 2)[ids], kg)
+        st_err = _oracle.state_err(g.state, o.state)
+        g.close()
+    f.close()
+    alg = 16.0 * N * N
+    return {"workload": f"cfg4 with unknown association: n={n_lm}, {meas_n / max(steps, 1):.1f} unlabelled measurements per step "
+                        f"against {n_lm} known landmarks",
+            "value": upd_n / (ms_total * 1e-3), "unit": UNIT, "measurements_per_s": meas_n / (ms_total * 1e-3),
+            "ms_per_measurement": ms_total / max(meas_n, 1), "updates_timed": int(upd_n), "measurements_timed": int(meas_n),
+            "parity": {"ok": bool(par_same and (st_err is None or st_err < PARITY_TOL)), "measurements_checked": par_meas,
+                       "association_indices_identical": par_same, "smallest_decision_margin": par_margin,
+                       "state_err": st_err, "tol": PARITY_TOL, "checker": "oracle/ekf_oracle.c in lockstep for the first two steps"},
+            "roofline": {"bound": "hbm", "kernel": "k_large_sweep_p<1> (one sweep per associated measurement)", "unit": "GB/s",
+                         "achieved": alg * upd_n / (ms_total * 1e-3) / 1e9, "peak": peak_gbs,
+                         "frac": alg * upd_n / (ms_total * 1e-3) / 1e9 / peak_gbs, "traffic": None,
+                         "note": "whole data_association() call incl. association kernels, gains and the host round trip "
+                                 "for the outputs; 16 N^2 B per applied correction"}}
+
+
+def scan_to_map_leg(pkg, device, B=8192, steps=12):
+    """cfg2 batched: 360-beam scans -> clustering + circle fit + classification -> data_association, one robot per
+    filter, everything on the device between the scan upload and the pose read-back."""
+    import torch
+    tg = pkg.tracegen
+    s = tg.simulate_scans(tg.default_world(N_SLOTS), B, steps + 3, seed=21)
+    cf = pkg.CircleFitting(device=device, max_scans=B, max_circles=16)
+    bt = pkg.EKFBatch(B, N_SLOTS, device=device)
+    M = 16
+    total_scans = 0
+    t_all = 0.0
+    upd0 = 0
+    for t in range(steps + 3):
+        if t == 3:
+            bt.sync()
+            upd0 = bt.update_count
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+        centers, counts = cf.run_batch(s["ranges"][t])      # host scans in, centres [B, 16, 2] + counts out
+        meas = np.ascontiguousarray(centers[:, :M, :])
+        cnt = np.minimum(counts, M).astype(np.int32)
+        bt.step_unknown(np.ascontiguousarray(s["twists"][t]), meas, cnt, M)
+        if t >= 3:
+            total_scans += B
+    bt.sync()
+    t_all = time.perf_counter() - t0
+    upd = bt.update_count - upd0
+    out = {"workload": f"cfg2 batched: {B} robots, scan -> circles -> data_association per step (host scans in, host poses out)",
+           "scans_per_s_e2e": total_scans / t_all, "updates_per_s": upd / t_all, "circles_per_scan": float(counts.mean()),
+           "steps": steps, "ms_per_step": 1e3 * t_all / steps}
+    bt.close()
+    cf.close()
+    return out
+
+
 def batch_unknown_leg(pkg, device, B, steps, warmup):
     """cfg3, unknown-association variant: prediction + data_association (Mahalanobis gating) per filter and step."""
     import torch
@@ -724,6 +895,9 @@ def run_ours(args):
             del d_tw, d_xy, d_vis
             torch.cuda.empty_cache()
             line["large_map"] = large_map_leg(pkg, local, args.large_n, args.large_updates, peak_gbs, want_cpu=True)
+            line["large_map_unknown"] = large_map_unknown_leg(pkg, local, args.large_n, peak_gbs)
+            line["single_filter"] = single_filter_leg(pkg, local)
+            line["scan_to_map"] = scan_to_map_leg(pkg, local)
             line["batch_unknown"] = batch_unknown_leg(pkg, local, B, K, W)
             line["laser"] = laser_leg(pkg, local)
             line["device_sim"] = device_sim_leg(pkg, local, B, K, W)
@@ -765,6 +939,7 @@ def main():
     ap.add_argument("--skip-large", action="store_true")
     ap.add_argument("--only-large", action="store_true", help="profiling aid: run just the cfg4 leg")
     ap.add_argument("--only-laser", action="store_true", help="profiling aid: run just the laser front-end leg")
+    ap.add_argument("--only-small", action="store_true", help="development aid: single_filter, large_map_unknown, scan_to_map")
     ap.add_argument("--sharded-n", type=int, default=40000, help="cfg5 landmarks (square number), N>1 only")
     ap.add_argument("--sharded-updates", type=int, default=96)
     args = ap.parse_args()
@@ -776,6 +951,11 @@ def main():
     elif args.only_laser:
         import ekf_slam_ml_b200 as pkg
         print(json.dumps(laser_leg(pkg, 0)))
+    elif args.only_small:
+        import ekf_slam_ml_b200 as pkg
+        print(json.dumps({"single_filter": single_filter_leg(pkg, 0),
+                          "large_map_unknown": large_map_unknown_leg(pkg, 0, args.large_n, measured_peaks()[0]),
+                          "scan_to_map": scan_to_map_leg(pkg, 0)}))
     else:
         run_ours(args)
 
