@@ -15,9 +15,16 @@
 #include "ekf_fused_sym.cuh"
 #include "ekf_fused_tile.cuh"
 #include "ekf_large.cuh"
-#include "ekf_large_tma.cuh"
+#include "ekf_large_mma.cuh"
 
 using namespace ekf;
+
+// multi-factor sweep: DMMA consumers (ekf_large_mma.cuh) unless the vector TMA path is asked for (comparison builds)
+#ifndef EKF_SWEEP_VECTOR
+#define EKF_SWEEP_LAUNCH launch_sweep_mma
+#else
+#define EKF_SWEEP_LAUNCH launch_sweep
+#endif
 
 namespace {
 
@@ -393,7 +400,7 @@ FusedParams fused_params(ekf_filter* h, int mode, int m_max) {
 // Apply the pending factors to Sigma in one sweep (ekf_large_delayed.cuh).
 int stream_flush(ekf_filter* h, int n_counted, const UpdateCmd* cmd) {
     if (h->pending == 0) return EKF_OK;
-    CU(launch_sweep(h->pending, h->d_sigma, h->ld, h->N, h->d_K2, h->d_W2, 0, h->d_nupd, n_counted, cmd, h->sm_count,
+    CU(EKF_SWEEP_LAUNCH(h->pending, h->d_sigma, h->ld, h->N, h->d_K2, h->d_W2, 0, h->d_nupd, n_counted, cmd, h->sm_count,
                       h->stream));
     h->launches += 1;
     h->sweeps += 1;

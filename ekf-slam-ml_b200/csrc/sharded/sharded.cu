@@ -15,9 +15,16 @@
 #include <vector>
 
 #include "../../../include/ekf_sharded_b200.h"
-#include "../ekf_large_tma.cuh"
+#include "../ekf_large_mma.cuh"
 
 using namespace ekf;
+
+// multi-factor sweep: DMMA consumers (ekf_large_mma.cuh) unless the vector TMA path is asked for (comparison builds)
+#ifndef EKF_SWEEP_VECTOR
+#define EKF_SWEEP_LAUNCH launch_sweep_mma
+#else
+#define EKF_SWEEP_LAUNCH launch_sweep
+#endif
 
 namespace {
 
@@ -494,7 +501,7 @@ int flush(ekf_sharded* h, int n_counted, bool use_cmd) {
     if (h->pending == 0) return 0;
     for (auto& s : h->sh) {
         if (s.rows > 0) {
-            CU(launch_sweep(h->pending, s.sig, h->ld, s.rows, s.K2, s.W2, s.r0, s.nupd, n_counted, use_cmd ? s.cmd : nullptr,
+            CU(EKF_SWEEP_LAUNCH(h->pending, s.sig, h->ld, s.rows, s.K2, s.W2, s.r0, s.nupd, n_counted, use_cmd ? s.cmd : nullptr,
                               h->sm_count, h->stream));
             h->launches++;
         }
