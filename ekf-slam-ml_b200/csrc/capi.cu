@@ -47,6 +47,23 @@ int fail(int code, const char* fmt, ...) {
         }                                                                                                \
     } while (0)
 
+// Launch with the programmatic-stream-serialization attribute (see pdl_prologue in ekf_large.cuh): only for kernels
+// that start with pdl_prologue().
+template <class... KArgs, class... Args>
+cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 constexpr int kFusedMaxN = 64;  // landmarks; Sigma (131^2 fp64 = 137 KB) must fit shared memory
 constexpr int kRing = 8;
 
@@ -412,10 +429,9 @@ int stream_flush(ekf_filter* h, int n_counted, const UpdateCmd* cmd) {
 // touched when kMaxPending factors have piled up or the verb ends.
 int stream_correct(ekf_filter* h, const double* pose_src, const UpdateCmd* cmd, int lm, double sx, double sy) {
     const int gb = (int)((h->ld + 255) / 256);
-    k_large_gain_p<<<gb, 256, 0, h->stream>>>(h->d_sigma, h->ld, h->N, h->d_state, h->d_state_alt, pose_src, cmd, lm, sx, sy,
-                                              h->d_K2, h->d_W2, h->pending);
+    CU(launch_pdl(k_large_gain_p, dim3(gb), dim3(kGainThreads), 0, h->stream, h->d_sigma, h->ld, h->N, h->d_state, h->d_state_alt,
+                  pose_src, cmd, lm, sx, sy, h->d_K2, h->d_W2, h->pending));
     h->launches += 1;
-    CU(cudaGetLastError());
     std::swap(h->d_state, h->d_state_alt);
     h->pending += 1;
     // a correction that data_association() may still drop (cmd != nullptr) is flushed by the caller, which passes
@@ -609,14 +625,13 @@ int ekf_predict(ekf_filter* h, double dtheta, double dx) {
         int rc = stream_flush(h, h->pending, nullptr);
         if (rc) return rc;
     }
-    k_large_motion<<<1, 32, 0, h->stream>>>(h->d_state, h->d_sigma, h->ld, dtheta, dx, h->d_motion);
-    k_large_predict_strips<<<(h->N - 3 + 255) / 256, 256, 0, h->stream>>>(h->d_sigma, h->ld, h->N, h->d_motion);
+    // motion model + robot block + the pending factors carried across the prediction (ekf_large_delayed.cuh), then
+    // the robot-landmark strips
+    CU(launch_pdl(k_large_motion, dim3(1), dim3(32), 0, h->stream, h->d_state, h->d_sigma, h->ld, dtheta, dx, h->d_motion,
+                  h->d_K2, h->d_W2, h->pending));
+    CU(launch_pdl(k_large_predict_strips, dim3((h->N - 3 + 255) / 256), dim3(256), 0, h->stream, h->d_sigma, h->ld, h->N,
+                  (const double*)h->d_motion));
     h->launches += 2;
-    if (h->pending > 0) {  // factors carried across the prediction (ekf_large_delayed.cuh)
-        k_large_predict_factors<<<1, 32, 0, h->stream>>>(h->d_K2, h->d_W2, h->ld, h->pending, h->d_motion);
-        h->launches += 1;
-    }
-    CU(cudaGetLastError());
     return EKF_OK;
 }
 

@@ -26,12 +26,40 @@ struct AssocPartial {
     int pad;
 };
 
+// Programmatic dependent launch (PDL): the streamed engine's short kernels form a serial chain on one stream, and a
+// correction is ~9 us of which a good part is launch latency.  A kernel launched with the programmatic-stream-
+// serialization attribute may be scheduled while its predecessor still runs; it must not touch the predecessor's
+// results before griddepcontrol.wait (which returns once the predecessor has completed and flushed).  Triggering the
+// dependents at entry is always safe for that reason.  Without the launch attribute both instructions are no-ops.
+__device__ __forceinline__ void pdl_prologue() {
+    asm volatile("griddepcontrol.launch_dependents;");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
 // ---------------------------------------------------------------- prediction (ekf_slam.cpp:55-106)
-// One thread: motion model, state[0..2], the 3x3 robot block of At*Sigma*At^T + Q, and (a1, a2) for the strips.
+// One warp: lane 0 does the motion model, state[0..2], the 3x3 robot block of At*Sigma*At^T + Q, and (a1, a2) for the
+// strips; lane j < pending carries pending factor j across the prediction (see k_large_predict_factors below).
 __global__ void k_large_motion(double* __restrict__ state, double* __restrict__ sig, long long ld, double dtheta,
-                               double dx, double* __restrict__ motion_out) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    const Motion m = motion_model(state[0], dtheta, dx);
+                               double dx, double* __restrict__ motion_out, double2* __restrict__ Kp,
+                               double2* __restrict__ Wp, int pending) {
+    pdl_prologue();
+    if (blockIdx.x != 0 || threadIdx.x >= 32) return;
+    Motion m = {};
+    if (threadIdx.x == 0) m = motion_model(state[0], dtheta, dx);
+    const double a1 = __shfl_sync(0xffffffffu, m.a1, 0), a2 = __shfl_sync(0xffffffffu, m.a2, 0);
+    {
+        const int j = threadIdx.x;
+        if (j < pending) {  // K_j[1] += a1 K_j[0], K_j[2] += a2 K_j[0]; likewise the columns 1, 2 of W_j
+            double2* K = Kp + (long long)j * ld;
+            double2* W = Wp + (long long)j * ld;
+            const double2 k0 = K[0], w0 = W[0];
+            K[1] = make_double2(fma(a1, k0.x, K[1].x), fma(a1, k0.y, K[1].y));
+            K[2] = make_double2(fma(a2, k0.x, K[2].x), fma(a2, k0.y, K[2].y));
+            W[1] = make_double2(fma(a1, w0.x, W[1].x), fma(a1, w0.y, W[1].y));
+            W[2] = make_double2(fma(a2, w0.x, W[2].x), fma(a2, w0.y, W[2].y));
+        }
+    }
+    if (threadIdx.x != 0) return;
     double s[3][3];
     for (int r = 0; r < 3; ++r)
         for (int c = 0; c < 3; ++c) s[r][c] = sig[r * ld + c];
@@ -58,6 +86,7 @@ __global__ void k_large_motion(double* __restrict__ state, double* __restrict__ 
 // Robot-landmark strips: rows 1,2 += a*row0 and cols 1,2 += a*col0 for indices k >= 3.  6N doubles touched.
 __global__ void k_large_predict_strips(double* __restrict__ sig, long long ld, int N,
                                        const double* __restrict__ motion) {
+    pdl_prologue();
     const int k = 3 + blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= N) return;
     const double a1 = motion[0], a2 = motion[1];

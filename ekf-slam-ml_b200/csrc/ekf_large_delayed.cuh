@@ -22,8 +22,6 @@ struct GainSharedP {
     Hj h;
     Sym2 si;
     double nu0, nu1;
-    int i3;
-    int active;
     double2 Kidx[kMaxPending][5];  // K_j[idx_a], a = 0..4
 };
 
@@ -37,38 +35,52 @@ __device__ __forceinline__ double apply_factor(double v, double2 k, double2 w) {
 // W = Hj Sigma comes from the five ROWS {0, 1, 2, 3+2i, 4+2i} of the current covariance (coalesced), rebuilt from
 // Sigma_0 and the pending factors; K = Sigma Hj^T S^-1 is formed as W^T S^-1 (ekf_slam.cpp:178 with Sigma = Sigma^T,
 // which the reference's (I - K H) Sigma keeps to rounding) so no strided column of Sigma is touched.
-// The O(1) part (S from the 5 x 5 block, its inverse, the innovation) is done by the first warp of every CTA with one
-// block entry per lane, so that its global loads are one round trip instead of a serial chain.
-__global__ void __launch_bounds__(256)
+//
+// CTA = 8 column warps + 1 scalar warp (kGainThreads = 288).  The scalar warp fetches the pending K pairs at the
+// five indices, releases the column warps (named barrier 1), and then does the O(1) part - S from the 5 x 5 block
+// with one block entry per lane, its inverse, the innovation with its two atan2 - while the column warps are
+// already streaming their five row entries and the pending W pairs; they meet again at named barrier 2.  The
+// scalar chain (~2.5 us of dependent latency) used to sit in front of everything.
+constexpr int kGainThreads = 288;
+__device__ __forceinline__ void named_bar_sync(int id, int count) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+
+__global__ void __launch_bounds__(kGainThreads)
     k_large_gain_p(const double* __restrict__ sig, long long ld, int N, const double* __restrict__ state_in,
                    double* __restrict__ state_out, const double* __restrict__ pose_src, const UpdateCmd* __restrict__ cmd,
                    int lm_arg, double sx_arg, double sy_arg, double2* __restrict__ Kp, double2* __restrict__ Wp, int p) {
     __shared__ GainSharedP g;
-    if (threadIdx.x < 32) {
-        const int lane = threadIdx.x;
-        int lm = lm_arg;
-        double sx = sx_arg, sy = sy_arg;
-        int active = 1;
-        if (cmd) {
-            active = cmd->do_update;
-            lm = cmd->lm;
-            sx = cmd->sx;
-            sy = cmd->sy;
-        }
-        if (lane == 0) g.active = active;
+    pdl_prologue();
+    int lm = lm_arg;
+    double sx = sx_arg, sy = sy_arg;
+    int active = 1;
+    if (cmd) {  // every thread reads the (tiny, uniform) command block itself
+        active = cmd->do_update;
+        lm = cmd->lm;
+        sx = cmd->sx;
+        sy = cmd->sy;
+    }
+    const int i3 = 3 + 2 * lm, i4 = i3 + 1;
+    if (threadIdx.x >= 256) {
+        // ------------------------------------------------------------ scalar warp
+        const int lane = threadIdx.x - 256;
         if (active) {
-            const int i3 = 3 + 2 * lm;
+            if (lane < 5) {
+                const long long ida = lane < 3 ? lane : i3 + (lane - 3);
+                for (int j = 0; j < p; ++j) g.Kidx[j][lane] = Kp[(long long)j * ld + ida];
+            }
+        }
+        __syncwarp();
+        named_bar_sync(1, kGainThreads);
+        if (active) {
             const int a = lane < 25 ? lane / 5 : 0, l = lane < 25 ? lane - 5 * (lane / 5) : 0;
             const long long ida = a < 3 ? a : i3 + (a - 3), idl = l < 3 ? l : i3 + (l - 3);
             const double theta = pose_src[0], x = pose_src[1], y = pose_src[2];
             const Hj h = make_hj(state_in[i3], state_in[i3 + 1], theta, x, y);
             double v = sig[ida * ld + idl];  // Sigma(id_a, id_l), then the pending factors in order
-            for (int j = 0; j < p; ++j) {
-                const double2 kja = Kp[(long long)j * ld + ida];
-                const double2 wjl = Wp[(long long)j * ld + idl];
-                v = apply_factor(v, kja, wjl);
-                if (l == 0 && lane < 25) g.Kidx[j][a] = kja;
-            }
+#pragma unroll 4
+            for (int j = 0; j < p; ++j) v = apply_factor(v, g.Kidx[j][a], Wp[(long long)j * ld + idl]);
             // column l of the block: s[a'] = Sigma(id_a', id_l) sits in lane 5 a' + l
             const double s0 = __shfl_sync(0xffffffffu, v, l), s1 = __shfl_sync(0xffffffffu, v, 5 + l),
                          s2 = __shfl_sync(0xffffffffu, v, 10 + l), s3 = __shfl_sync(0xffffffffu, v, 15 + l),
@@ -91,33 +103,43 @@ __global__ void __launch_bounds__(256)
                 range_bearing(sx, sy, zr, zphi);
                 g.nu0 = __dsub_rn(zr, h.zr);
                 g.nu1 = normalize_angle(__dsub_rn(zphi, h.zphi));
-                g.i3 = i3;
             }
         }
+        __syncwarp();
+        named_bar_sync(2, kGainThreads);
+        return;
     }
-    __syncthreads();
-    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= ld) return;
+    // ---------------------------------------------------------------- column warps
+    const long long k = (long long)blockIdx.x * 256 + threadIdx.x;
+    const bool in_range = k < ld, live = in_range && k < N && active;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0, s4 = 0.0, st_k = 0.0;
+    if (live) {  // in flight while the scalar warp fetches the K pairs
+        s0 = sig[k], s1 = sig[ld + k], s2 = sig[2 * ld + k], s3 = sig[i3 * ld + k], s4 = sig[i4 * ld + k];
+        st_k = state_in[k];
+    }
+    named_bar_sync(1, kGainThreads);
+    if (live) {
+#pragma unroll 4
+        for (int j = 0; j < p; ++j) {
+            const double2 wj = Wp[(long long)j * ld + k];  // W_j[:, k]
+            s0 = apply_factor(s0, g.Kidx[j][0], wj);
+            s1 = apply_factor(s1, g.Kidx[j][1], wj);
+            s2 = apply_factor(s2, g.Kidx[j][2], wj);
+            s3 = apply_factor(s3, g.Kidx[j][3], wj);
+            s4 = apply_factor(s4, g.Kidx[j][4], wj);
+        }
+    }
+    named_bar_sync(2, kGainThreads);
+    if (!in_range) return;
     double2* Kout = Kp + (long long)p * ld;
     double2* Wout = Wp + (long long)p * ld;
-    if (k >= N || !g.active) {  // padding entries and dropped measurements contribute a zero factor
+    if (!live) {  // padding entries and dropped measurements contribute a zero factor
         Kout[k] = make_double2(0.0, 0.0);
         Wout[k] = make_double2(0.0, 0.0);
         if (k < N) state_out[k] = state_in[k];
         return;
     }
     const Hj h = g.h;
-    const int i3 = g.i3, i4 = i3 + 1;
-    double s0 = sig[k], s1 = sig[ld + k], s2 = sig[2 * ld + k], s3 = sig[i3 * ld + k], s4 = sig[i4 * ld + k];
-    const double st_k = state_in[k];
-    for (int j = 0; j < p; ++j) {
-        const double2 wj = Wp[(long long)j * ld + k];  // W_j[:, k]
-        s0 = apply_factor(s0, g.Kidx[j][0], wj);
-        s1 = apply_factor(s1, g.Kidx[j][1], wj);
-        s2 = apply_factor(s2, g.Kidx[j][2], wj);
-        s3 = apply_factor(s3, g.Kidx[j][3], wj);
-        s4 = apply_factor(s4, g.Kidx[j][4], wj);
-    }
     const double p0 = h_row0(h, s1, s2, s3, s4), p1 = h_row1(h, s0, s1, s2, s3, s4);
     Wout[k] = make_double2(p0, p1);
     const double k0 = fma(p1, g.si.i10, p0 * g.si.i00);

@@ -23,9 +23,13 @@
 
 namespace ekf {
 
+#ifndef EKF_MMA_STAGES
+#define EKF_MMA_STAGES 4
+#endif
+constexpr int kMmaStages = EKF_MMA_STAGES;   // 4 x (33 KB tile + K rows); 6 stages measured slower (748 vs 727 us at P = 14)
 constexpr int kMmaRowStride = kTmaCols + 8;  // doubles: 4,160 B = 64 B past a multiple of 128 B
 constexpr int kMmaTileBytes = kStageRows * kMmaRowStride * 8;
-constexpr int kMmaSmemBytes = kStages * (kMmaTileBytes + kKBytes) + 3 * kStages * 8 + 64;
+constexpr int kMmaSmemBytes = kMmaStages * (kMmaTileBytes + kKBytes) + 3 * kMmaStages * 8 + 64;
 
 template <int P>
 __global__ void __launch_bounds__(kTmaThreads, 1)
@@ -34,17 +38,18 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
                       int n_counted, const UpdateCmd* __restrict__ cmd) {
     constexpr int KS = (2 * P + 3) / 4;  // DMMA k-steps
     constexpr int NBW = 8;               // 8 x 8 blocks per consumer warp and stage (64 columns)
+    pdl_prologue();
     if (cmd && !cmd->do_update) return;
     if (blockIdx.x == 0 && threadIdx.x == 0 && n_updates) *n_updates += (unsigned long long)n_counted;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    double* tiles = reinterpret_cast<double*>(smem_raw);                                     // [kStages][8][520]
-    double2* ksm = reinterpret_cast<double2*>(smem_raw + (size_t)kStages * kMmaTileBytes);   // [kStages][kMaxPending][8]
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)kStages * (kMmaTileBytes + kKBytes));
-    uint64_t* done = full + kStages;
-    uint64_t* empty = done + kStages;
+    double* tiles = reinterpret_cast<double*>(smem_raw);                                     // [kMmaStages][8][520]
+    double2* ksm = reinterpret_cast<double2*>(smem_raw + (size_t)kMmaStages * kMmaTileBytes);   // [kMmaStages][kMaxPending][8]
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)kMmaStages * (kMmaTileBytes + kKBytes));
+    uint64_t* done = full + kMmaStages;
+    uint64_t* empty = done + kMmaStages;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) {
-        for (int s = 0; s < kStages; ++s) {
+        for (int s = 0; s < kMmaStages; ++s) {
             mbar_init(full + s, 1);
             mbar_init(done + s, kTmaConsumerWarps);
             mbar_init(empty + s, 1);
@@ -81,7 +86,7 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
                     for (int j = 0; j < P; ++j)
                         bulk_g2s(ksm + ((size_t)stage * kMaxPending + j) * kStageRows, Kp + (long long)j * ld + row0 + r,
                                  kStageRows * 16, full + stage);
-                    if (++stage == kStages) {
+                    if (++stage == kMmaStages) {
                         stage = 0;
                         phase ^= 1u;
                     }
@@ -137,7 +142,7 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
                 fence_proxy_async_smem();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(done + stage);
-                if (++stage == kStages) {
+                if (++stage == kMmaStages) {
                     stage = 0;
                     phase ^= 1u;
                 }
@@ -154,9 +159,9 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
                         bulk_s2g(sig + (long long)(r + k) * ld + c0, tile + k * kMmaRowStride, (uint32_t)(width * 8));
                     bulk_commit();
                     bulk_wait_read_1();  // every store but the newest has finished reading shared memory
-                    if (!first) mbar_arrive(empty + (stage == 0 ? kStages - 1 : stage - 1));
+                    if (!first) mbar_arrive(empty + (stage == 0 ? kMmaStages - 1 : stage - 1));
                     first = false;
-                    if (++stage == kStages) {
+                    if (++stage == kMmaStages) {
                         stage = 0;
                         phase ^= 1u;
                     }
