@@ -392,7 +392,7 @@ def sharded_map_leg(pkg, dist, local, n_lm, timed_updates, peak_gbs):
         "workload": f"cfg5: single map, n={n_lm} landmarks (N={N}, Sigma {8.0 * N * N / 1e9:.1f} GB) row-block-sharded over "
                     f"{world} GPUs; per correction: one NCCL all-reduce of W (2N fp64), K = W^T S^-1 formed on every rank, sweep of own rows",
         "value": 1e3 / ms_upd, "unit": UNIT, "updates_timed": done, "ms_per_update": ms_upd,
-        "gpu_launches_rank0": int(f.launch_count - l0), "rows_rank0": list(rows),
+        "gpu_launches_rank0": int(f.launch_count - l0), "rows_rank0": list(rows), "w_exchange": getattr(f, "exchange", "nccl all-reduce"),
         "roofline": {"bound": "hbm", "kernel": "k_large_sweep_p<P> on each rank's rows (time per sweep = whole step incl. "
                                                 "prediction, gains and the NCCL exchanges)",
                      "achieved": per_gpu_bytes * n_sweeps / (total_ms * 1e-3) / 1e9, "peak": peak_gbs, "unit": "GB/s per GPU",
@@ -939,6 +939,7 @@ def main():
     ap.add_argument("--skip-large", action="store_true")
     ap.add_argument("--only-large", action="store_true", help="profiling aid: run just the cfg4 leg")
     ap.add_argument("--only-laser", action="store_true", help="profiling aid: run just the laser front-end leg")
+    ap.add_argument("--only-sharded", action="store_true", help="development aid (under torchrun): just the cfg5 leg")
     ap.add_argument("--only-small", action="store_true", help="development aid: single_filter, large_map_unknown, scan_to_map")
     ap.add_argument("--sharded-n", type=int, default=40000, help="cfg5 landmarks (square number), N>1 only")
     ap.add_argument("--sharded-updates", type=int, default=96)
@@ -951,6 +952,18 @@ def main():
     elif args.only_laser:
         import ekf_slam_ml_b200 as pkg
         print(json.dumps(laser_leg(pkg, 0)))
+    elif args.only_sharded:
+        import torch
+        import torch.distributed as dist
+        import ekf_slam_ml_b200 as pkg
+        local = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        out = sharded_map_leg(pkg, dist, local, args.sharded_n, args.sharded_updates, measured_peaks()[0])
+        if dist.get_rank() == 0:
+            print(json.dumps(out), flush=True)
+        dist.barrier()
+        dist.destroy_process_group()
     elif args.only_small:
         import ekf_slam_ml_b200 as pkg
         print(json.dumps({"single_filter": single_filter_leg(pkg, 0),

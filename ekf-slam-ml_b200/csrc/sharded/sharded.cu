@@ -196,6 +196,167 @@ __global__ void __launch_bounds__(256)
     state[k] = ns;
 }
 
+// ---- the W exchange without a collective ("push") ----------------------------------------------------------------
+// Only two ranks hold rows that enter W = Hj Sigma: rank 0 (robot rows 0..2) and the owner of landmark i.  Instead of
+// an all-reduce of a 2 ld vector of which at most two contributions are non-zero, those two ranks store their partial
+// W straight into every rank's exchange buffer over NVLink - through the NVSwitch multicast address when there is one
+// (one store, replicated by the switch), else peer by peer - and raise a flag; every rank then adds the two partials
+// inside the gain kernel, which waits on the flags instead of on a collective.
+// Exchange buffer per rank (symmetric, allocated by the caller, see ekf_sharded_attach_exchange):
+//   flags [kMaxPending][2] uint64 (pad to 256 B) | data [kMaxPending][2][ld] double2
+// Slot p = the pending-factor slot of the correction, source 0 = rank 0's partial, source 1 = the landmark owner's.  A flag
+// holds the group generation number of the data it guards; slots are reused only after the group's sweep, which is
+// preceded by a barrier across the ranks.
+constexpr size_t kXFlagBytes = 256;
+__host__ __device__ inline size_t xdata_index(int p, int src, long long ld) { return ((size_t)p * 2 + src) * (size_t)ld; }
+
+__device__ __forceinline__ void st_sys_v2(double2* ptr, double2 v) {  // also valid on a multicast address
+    asm volatile("st.relaxed.sys.global.v2.f64 [%0], {%1, %2};" ::"l"(ptr), "d"(v.x), "d"(v.y) : "memory");
+}
+__device__ __forceinline__ void mc_st_v2(double2* ptr, double2 v) {
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(ptr),
+                 "r"(__double2loint(v.x)), "r"(__double2hiint(v.x)), "r"(__double2loint(v.y)), "r"(__double2hiint(v.y))
+                 : "memory");
+}
+__device__ __forceinline__ void st_release_sys_u64(unsigned long long* ptr, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(ptr), "l"(v) : "memory");
+}
+__device__ __forceinline__ void mc_st_release_u64(unsigned long long* ptr, unsigned long long v) {
+    asm volatile("fence.acq_rel.sys;" ::: "memory");
+    asm volatile("multimem.st.relaxed.sys.global.u64 [%0], %1;" ::"l"(ptr), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long* ptr) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(ptr) : "memory");
+    return v;
+}
+
+struct XPeers {
+    unsigned char* base[8];  // every rank's exchange buffer as mapped here (index = rank)
+    unsigned char* mc;       // multicast address of the same buffer, or null
+    int world;
+};
+
+// k_sh_wpart + push: this rank's partial W goes to every rank's slot instead of a local array.
+__global__ void __launch_bounds__(256)
+    k_sh_wpart_push(const double* __restrict__ sig_local, long long ld, long long r0, long long r1, int N, int rank,
+                    const Ctx* __restrict__ ctx, const double2* __restrict__ Kp, const double2* __restrict__ Wp, int p,
+                    const XPeers xp, unsigned long long gen, unsigned int* __restrict__ done_counter) {
+    pdl_prologue();
+    const int active = ctx->active;
+    const long long i3 = ctx->i3;
+    const bool owns_lm = active && i3 >= r0 && i3 < r1;
+    // rank 0 always reports source 0 (zeros when the measurement was dropped) and, when it owns the landmark too or
+    // nothing is applied, source 1 as well; any other rank reports source 1 when it owns the landmark
+    const bool push0 = rank == 0, push1 = rank == 0 ? (owns_lm || !active) : owns_lm;
+    if (!push0 && !push1) return;
+    const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < ld) {
+        double2 w = make_double2(0.0, 0.0);
+        if (c < N && active) {
+            const long long id[5] = {0, 1, 2, i3, i3 + 1};
+            double sv[5];
+#pragma unroll
+            for (int k = 0; k < 5; ++k) {
+                double v = 0.0;
+                if (id[k] >= r0 && id[k] < r1) {
+                    v = sig_local[(id[k] - r0) * ld + c];
+                    for (int j = 0; j < p; ++j) v = apply_factor(v, Kp[(long long)j * ld + id[k]], Wp[(long long)j * ld + c]);
+                }
+                sv[k] = v;
+            }
+            const Hj h = ctx->h;
+            w = make_double2(h_row0(h, sv[1], sv[2], sv[3], sv[4]), h_row1(h, sv[0], sv[1], sv[2], sv[3], sv[4]));
+        }
+        // rank 0 owning the landmark: its partial is the whole W (source 0) and source 1 is zero
+        const double2 zero = make_double2(0.0, 0.0);
+        const size_t o0 = kXFlagBytes + (xdata_index(p, 0, ld) + (size_t)c) * sizeof(double2);
+        const size_t o1 = kXFlagBytes + (xdata_index(p, 1, ld) + (size_t)c) * sizeof(double2);
+        if (xp.mc) {
+            if (push0) mc_st_v2(reinterpret_cast<double2*>(xp.mc + o0), w);
+            if (push1) mc_st_v2(reinterpret_cast<double2*>(xp.mc + o1), rank == 0 ? zero : w);
+        } else {
+            for (int g = 0; g < xp.world; ++g) {
+                if (push0) st_sys_v2(reinterpret_cast<double2*>(xp.base[g] + o0), w);
+                if (push1) st_sys_v2(reinterpret_cast<double2*>(xp.base[g] + o1), rank == 0 ? zero : w);
+            }
+        }
+    }
+    // every CTA's stores are ordered before the flag: fence, count the CTA in, the last one raises the flags
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x != 0) return;
+    if (atomicAdd(done_counter, 1u) != gridDim.x - 1) return;
+    *done_counter = 0;
+    __threadfence_system();
+    for (int src = 0; src < 2; ++src) {
+        if (!(src == 0 ? push0 : push1)) continue;
+        const size_t of = ((size_t)p * 2 + src) * sizeof(unsigned long long);
+        if (xp.mc) {
+            mc_st_release_u64(reinterpret_cast<unsigned long long*>(xp.mc + of), gen);
+        } else {
+            for (int g = 0; g < xp.world; ++g) st_release_sys_u64(reinterpret_cast<unsigned long long*>(xp.base[g] + of), gen);
+        }
+    }
+}
+
+// k_sh_gain_state fed by the pushed partials: waits for both sources' flags, W = source 0 + source 1 (the all-reduce's
+// sum: every other rank contributes exact zeros), then K, the state update and the W slot as before.
+__global__ void __launch_bounds__(256)
+    k_sh_gain_state_push(const unsigned char* __restrict__ xlocal, int p, unsigned long long gen, double2* __restrict__ Wslot,
+                         double2* __restrict__ Kout, double* __restrict__ state, const Ctx* __restrict__ ctx, int N,
+                         long long ld) {
+    __shared__ Sym2 si_s;
+    __shared__ double nu_s[2];
+    __shared__ int active_s;
+    pdl_prologue();
+    const double2* x0 = reinterpret_cast<const double2*>(xlocal + kXFlagBytes) + xdata_index(p, 0, ld);
+    const double2* x1 = reinterpret_cast<const double2*>(xlocal + kXFlagBytes) + xdata_index(p, 1, ld);
+    if (threadIdx.x == 0) {
+        const unsigned long long* fl = reinterpret_cast<const unsigned long long*>(xlocal) + (size_t)p * 2;
+        while (ld_acquire_sys_u64(fl) != gen) {
+        }
+        while (ld_acquire_sys_u64(fl + 1) != gen) {
+        }
+        active_s = ctx->active;
+        if (active_s) {
+            const Hj h = ctx->h;
+            const int i3 = ctx->i3;
+            double2 w5[5];
+            const int id[5] = {0, 1, 2, i3, i3 + 1};
+#pragma unroll
+            for (int k = 0; k < 5; ++k) {
+                const double2 a = __ldcg(x0 + id[k]), b = __ldcg(x1 + id[k]);
+                w5[k] = make_double2(a.x + b.x, a.y + b.y);
+            }
+            const double s00 = h_row0(h, w5[1].x, w5[2].x, w5[3].x, w5[4].x) + kR;
+            const double s01 = h_row1(h, w5[0].x, w5[1].x, w5[2].x, w5[3].x, w5[4].x);
+            const double s10 = h_row0(h, w5[1].y, w5[2].y, w5[3].y, w5[4].y);
+            const double s11 = h_row1(h, w5[0].y, w5[1].y, w5[2].y, w5[3].y, w5[4].y) + kR;
+            si_s = inv2x2(s00, s01, s10, s11);
+            nu_s[0] = __dsub_rn(ctx->zr, h.zr);
+            nu_s[1] = normalize_angle(__dsub_rn(ctx->zphi, h.zphi));
+        }
+    }
+    __syncthreads();
+    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= ld) return;
+    if (k >= N || !active_s) {
+        Wslot[k] = make_double2(0.0, 0.0);
+        Kout[k] = make_double2(0.0, 0.0);
+        return;
+    }
+    const double2 a = __ldcg(x0 + k), b = __ldcg(x1 + k);
+    const double2 w = make_double2(a.x + b.x, a.y + b.y);
+    Wslot[k] = w;
+    const Sym2 si = si_s;
+    const double k0 = fma(w.y, si.i10, w.x * si.i00), k1 = fma(w.y, si.i11, w.x * si.i01);
+    Kout[k] = make_double2(k0, k1);
+    double ns = state[k] + fma(k1, nu_s[1], k0 * nu_s[0]);
+    if (k == 0) ns = normalize_angle(ns);  // ekf_slam.cpp:187
+    state[k] = ns;
+}
+
 // ---- association
 __global__ void __launch_bounds__(256)
     k_sh_assoc_local(const double* __restrict__ robot, const double* __restrict__ sig_local, long long ld, long long r0,
@@ -351,9 +512,32 @@ struct ekf_sharded {
     cudaEvent_t t0 = nullptr, t1 = nullptr;
     unsigned char* h_stage = nullptr;  // pinned
     size_t h_stage_bytes = 0;
+    // push exchange of W (ekf_sharded_attach_exchange); the buffers belong to the caller
+    bool push = false;
+    XPeers xp = {};
+    unsigned char* xlocal = nullptr;
+    unsigned long long gen = 1;     // group generation: what a raised flag holds
+    unsigned int* d_done2 = nullptr;
+    int* d_barrier = nullptr;
+    int rank = 0;
 };
 
 namespace {
+
+template <class... KArgs, class... Args>
+cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 
 struct Dev {
     int prev = -1;
@@ -499,6 +683,12 @@ int exchange_partials(ekf_sharded* h) {
 // apply the pending factors to every shard's own rows in one sweep
 int flush(ekf_sharded* h, int n_counted, bool use_cmd) {
     if (h->pending == 0) return 0;
+    if (h->push) {
+        // the exchange slots are reused by the next group: no rank may still be reading this group's partials when
+        // the first push of the next group lands (a 4-byte all-reduce as the barrier, once per sweep)
+        NC(ncclAllReduce(h->d_barrier, h->d_barrier, 1, ncclInt, ncclSum, h->comm, h->stream));
+        h->gen += 1;
+    }
     for (auto& s : h->sh) {
         if (s.rows > 0) {
             CU(EKF_SWEEP_LAUNCH(h->pending, s.sig, h->ld, s.rows, s.K2, s.W2, s.r0, s.nupd, n_counted, use_cmd ? s.cmd : nullptr,
@@ -518,6 +708,18 @@ int settle(ekf_sharded* h) { return h->pending ? flush(h, h->pending, false) : 0
 int correct(ekf_sharded* h, bool use_cmd, bool stale_pose, int lm, double sx, double sy) {
     const int gl = (int)((h->ld + 255) / 256);
     const int p = h->pending;
+    if (h->push) {
+        Shard& s = h->sh[0];
+        k_sh_ctx_h<<<1, 32, 0, h->stream>>>(s.state, stale_pose ? s.pose0 : s.state, use_cmd ? s.cmd : nullptr, lm, sx, sy, s.ctx);
+        CU(launch_pdl(k_sh_wpart_push, dim3(gl), dim3(256), 0, h->stream, (const double*)s.sig, h->ld, s.r0, s.r1, h->N, h->rank,
+                      (const Ctx*)s.ctx, (const double2*)s.K2, (const double2*)s.W2, p, h->xp, h->gen, h->d_done2));
+        CU(launch_pdl(k_sh_gain_state_push, dim3(gl), dim3(256), 0, h->stream, (const unsigned char*)h->xlocal, p, h->gen,
+                      s.W2 + (long long)p * h->ld, s.K2 + (long long)p * h->ld, s.state, (const Ctx*)s.ctx, h->N, h->ld));
+        h->launches += 3;
+        h->pending += 1;
+        if (!use_cmd && h->pending == kMaxPending) return flush(h, kMaxPending, false);
+        return 0;
+    }
     for (auto& s : h->sh) {
         k_sh_ctx_h<<<1, 32, 0, h->stream>>>(s.state, stale_pose ? s.pose0 : s.state, use_cmd ? s.cmd : nullptr, lm, sx, sy, s.ctx);
         k_sh_wpart<<<gl, 256, 0, h->stream>>>(s.sig, h->ld, s.r0, s.r1, h->N, s.ctx, s.K2, s.W2, p, s.Wpart);
@@ -627,6 +829,8 @@ int ekf_sharded_destroy(ekf_sharded* h) {
         cudaFree(s.d_created);
     }
     if (h->d_srcs) cudaFree((void*)h->d_srcs);
+    cudaFree(h->d_done2);
+    cudaFree(h->d_barrier);
     if (h->h_stage) cudaFreeHost(h->h_stage);
     if (h->comm) ncclCommDestroy(h->comm);
     if (h->t0) cudaEventDestroy(h->t0);
@@ -656,6 +860,7 @@ int ekf_sharded_create(int n, int rank, int world, const void* id128, int device
         ekf_sharded_destroy(h);
         return fail(1000 + (int)r, "ncclCommInitRank: %s", ncclGetErrorString(r));
     }
+    h->rank = rank;
     h->sh.resize(1);
     rc = alloc_shard(h, h->sh[0], rank);
     if (!rc) rc = finish_create(h);
@@ -664,6 +869,42 @@ int ekf_sharded_create(int n, int rank, int world, const void* id128, int device
         return rc;
     }
     *out = h;
+    return 0;
+}
+
+// Push exchange of W (see k_sh_wpart_push): the caller provides one symmetric buffer per rank - e.g. from
+// torch.distributed._symmetric_memory or cudaIpc handles - of ekf_sharded_exchange_bytes() bytes, zero-filled, mapped
+// into this process for every rank (peer_bases[rank'], rank' = 0..world-1), plus the multicast address of the same
+// buffer when the fabric has one (0 otherwise).  Collective: every rank attaches before the next verb.  The buffers
+// stay the caller's; they must outlive the handle.  Without this call the exchange is an ncclAllReduce.
+int ekf_sharded_exchange_bytes(ekf_sharded* h, uint64_t* bytes) {
+    if (!h || !bytes) return fail(-1, "null argument");
+    *bytes = kXFlagBytes + (uint64_t)kMaxPending * 2 * (uint64_t)h->ld * sizeof(double2);
+    return 0;
+}
+int ekf_sharded_attach_exchange(ekf_sharded* h, int world, const uint64_t* peer_bases, uint64_t multicast_base) {
+    if (!h || !peer_bases) return fail(-1, "null argument");
+    if (h->local) return fail(-1, "the push exchange needs real ranks (not the single-GPU emulation)");
+    if (world != h->world || world > 8) return fail(-1, "push exchange: world size %d not supported", world);
+    Dev g(h->device);
+    {
+        int rc_ = settle(h);
+        if (rc_) return rc_;
+    }
+    CU(cudaStreamSynchronize(h->stream));
+    h->xp = XPeers{};
+    for (int r = 0; r < world; ++r) h->xp.base[r] = reinterpret_cast<unsigned char*>((uintptr_t)peer_bases[r]);
+    h->xp.mc = reinterpret_cast<unsigned char*>((uintptr_t)multicast_base);
+    h->xp.world = world;
+    h->xlocal = h->xp.base[h->rank];
+    if (!h->d_done2) {
+        CU(cudaMalloc(&h->d_done2, sizeof(unsigned int)));
+        CU(cudaMalloc(&h->d_barrier, sizeof(int)));
+        CU(cudaMemset(h->d_done2, 0, sizeof(unsigned int)));
+        CU(cudaMemset(h->d_barrier, 0, sizeof(int)));
+    }
+    h->gen = 1;
+    h->push = true;
     return 0;
 }
 

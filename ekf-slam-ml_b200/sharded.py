@@ -2,6 +2,7 @@
 covariance does not fit — or should not live — on one GPU (BASELINE.json cfg5).  One process per GPU; every rank calls
 every verb with the same arguments."""
 import ctypes
+import os
 
 import numpy as np
 
@@ -40,7 +41,35 @@ class ShardedEKF:
         idbuf = ctypes.create_string_buffer(box[0], 128)
         h = ctypes.c_void_p()
         _check(L.ekf_sharded_create(int(n), rank, world, idbuf, int(device), ctypes.byref(h)))
-        return cls(h, n, world, False)
+        self = cls(h, n, world, False)
+        self.exchange = "nccl all-reduce"
+        if os.environ.get("EKF_SHARDED_EXCHANGE", "push") != "nccl":
+            self._attach_push_exchange(dist, device)
+        return self
+
+    def _attach_push_exchange(self, dist, device):
+        """Symmetric exchange buffers (peer-mapped, multicast where the fabric has it) from torch's symmetric memory;
+        on any failure the handle simply keeps the NCCL all-reduce."""
+        try:
+            import torch
+            import torch.distributed._symmetric_memory as symm_mem
+            nbytes = ctypes.c_uint64()
+            _check(self._L.ekf_sharded_exchange_bytes(self._h, ctypes.byref(nbytes)))
+            buf = symm_mem.empty((nbytes.value + 7) // 8, dtype=torch.float64, device=torch.device("cuda", device))
+            buf.zero_()
+            hdl = symm_mem.rendezvous(buf, dist.group.WORLD)
+            torch.cuda.synchronize(device)
+            dist.barrier()
+            peers = (ctypes.c_uint64 * self.world)(*[int(p) for p in hdl.buffer_ptrs])
+            mc = int(hdl.multicast_ptr) if getattr(hdl, "multicast_ptr", 0) else 0
+            if os.environ.get("EKF_SHARDED_EXCHANGE") == "push-unicast":
+                mc = 0
+            _check(self._L.ekf_sharded_attach_exchange(self._h, self.world, peers, ctypes.c_uint64(mc)))
+            self._xbuf, self._xhdl = buf, hdl
+            self.exchange = "push over NVLink (%s)" % ("NVSwitch multicast" if mc else "peer stores")
+        except Exception as e:  # noqa: BLE001 - optional fast path
+            import sys
+            sys.stderr.write(f"[ekf_sharded] push exchange unavailable, keeping the NCCL all-reduce: {e!r}\n")
 
     def close(self):
         if getattr(self, "_h", None):

@@ -31,6 +31,15 @@ int ekf_sharded_create(int n_landmarks, int rank, int world, const void* id128, 
  * arithmetic be parity-tested on a single GPU, as B200_PROFILING.md asks for when ranks outnumber GPUs */
 int ekf_sharded_create_local(int n_landmarks, int world, int device, ekf_sharded** out);
 int ekf_sharded_destroy(ekf_sharded* h);
+/* Optional: exchange W without a collective.  Per correction only rank 0 (robot rows) and the landmark's owner hold
+ * non-zero parts of W = Hj*Sigma; with an attached exchange buffer they store their parts straight into every rank's
+ * buffer over NVLink (through the NVSwitch multicast address when one is given) and the gain kernel waits on flags
+ * instead of on an ncclAllReduce.  The caller allocates one symmetric, zero-filled buffer of
+ * ekf_sharded_exchange_bytes() bytes per rank (e.g. torch.distributed._symmetric_memory, or cudaIpc) and passes every
+ * rank's mapping of it (peer_bases[0..world-1]) and the multicast address (0 = none).  Collective; the buffers must
+ * outlive the handle.  Results are identical to the all-reduce path. */
+int ekf_sharded_exchange_bytes(ekf_sharded* h, uint64_t* bytes);
+int ekf_sharded_attach_exchange(ekf_sharded* h, int world, const uint64_t* peer_bases, uint64_t multicast_base);
 
 int ekf_sharded_predict(ekf_sharded* h, double dtheta, double dx);                         /* ekf_slam.cpp:55-106  */
 int ekf_sharded_measurement(ekf_sharded* h, const double* xy, const uint8_t* visible);     /* ekf_slam.cpp:108-197 */
