@@ -138,7 +138,7 @@ SIGNATURES_SHARDED = {
     "ekf_sharded_create_local": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int, c_void_pp]),
     "ekf_sharded_destroy": (ctypes.c_int, [ctypes.c_void_p]),
     "ekf_sharded_predict": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_double, ctypes.c_double]),
-    "ekf_sharded_measurement": (ctypes.c_int, [ctypes.c_void_p, c_double_p, c_u8_p]),
+    "ekf_sharded_measurement": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     "ekf_sharded_data_association": (ctypes.c_int, [ctypes.c_void_p, c_double_p, ctypes.c_int, c_u8_p, c_i32_p,
                                                     c_double_p, c_double_p, c_u8_p]),
     "ekf_sharded_get_state": (ctypes.c_int, [ctypes.c_void_p, c_double_p]),

@@ -60,9 +60,25 @@ struct Ctx {
 
 // ---- prediction
 __global__ void k_sh_motion(double* __restrict__ state, double* __restrict__ sig_robot, long long ld, double dtheta,
-                            double dx, double* __restrict__ motion_out) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    const Motion m = motion_model(state[0], dtheta, dx);
+                            double dx, double* __restrict__ motion_out, double2* __restrict__ Kp,
+                            double2* __restrict__ Wp, int pending) {
+    if (blockIdx.x != 0 || threadIdx.x >= 32) return;
+    Motion m = {};
+    if (threadIdx.x == 0) m = motion_model(state[0], dtheta, dx);
+    {   // lane j < pending carries factor j across the prediction: A K_j, W_j A^T (ekf_large_delayed.cuh)
+        const double a1 = __shfl_sync(0xffffffffu, m.a1, 0), a2 = __shfl_sync(0xffffffffu, m.a2, 0);
+        const int j = threadIdx.x;
+        if (j < pending) {
+            double2* K = Kp + (long long)j * ld;
+            double2* W = Wp + (long long)j * ld;
+            const double2 k0 = K[0], w0 = W[0];
+            K[1] = make_double2(fma(a1, k0.x, K[1].x), fma(a1, k0.y, K[1].y));
+            K[2] = make_double2(fma(a2, k0.x, K[2].x), fma(a2, k0.y, K[2].y));
+            W[1] = make_double2(fma(a1, w0.x, W[1].x), fma(a1, w0.y, W[1].y));
+            W[2] = make_double2(fma(a2, w0.x, W[2].x), fma(a2, w0.y, W[2].y));
+        }
+    }
+    if (threadIdx.x != 0) return;
     if (sig_robot) {  // the rank that owns rows 0..2 also owns the 3x3 robot block
         double s[3][3];
         for (int r = 0; r < 3; ++r)
@@ -237,35 +253,70 @@ struct XPeers {
     int world;
 };
 
-// k_sh_wpart + push: this rank's partial W goes to every rank's slot instead of a local array.
+// k_sh_ctx_h + k_sh_wpart + push in one launch: thread 0 of block 0 writes the correction's context (for the gain
+// kernel that follows); on the ranks that own rows entering W the first warp of every CTA forms H_j and fetches the
+// pending K pairs at the owned rows, then each thread rebuilds its column of the owned rows (one W load per pending
+// factor) and stores the partial W into every rank's slot.
 __global__ void __launch_bounds__(256)
     k_sh_wpart_push(const double* __restrict__ sig_local, long long ld, long long r0, long long r1, int N, int rank,
-                    const Ctx* __restrict__ ctx, const double2* __restrict__ Kp, const double2* __restrict__ Wp, int p,
-                    const XPeers xp, unsigned long long gen, unsigned int* __restrict__ done_counter) {
+                    const double* __restrict__ state, const double* __restrict__ pose_src, const UpdateCmd* __restrict__ cmd,
+                    int lm_arg, double sx_arg, double sy_arg, Ctx* __restrict__ ctx_out, const double2* __restrict__ Kp,
+                    const double2* __restrict__ Wp, int p, const XPeers xp, unsigned long long gen,
+                    unsigned int* __restrict__ done_counter) {
+    __shared__ Hj h_s;
+    __shared__ double2 kidx_s[kMaxPending][5];
     pdl_prologue();
-    const int active = ctx->active;
-    const long long i3 = ctx->i3;
+    int lm = lm_arg, active = 1;
+    double sx = sx_arg, sy = sy_arg;
+    if (cmd) {
+        active = cmd->do_update;
+        lm = cmd->lm;
+        sx = cmd->sx;
+        sy = cmd->sy;
+    }
+    const long long i3 = 3 + 2 * (long long)lm;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {  // every rank: the context the gain kernel reads
+        ctx_out->active = active;
+        if (active) {
+            ctx_out->i3 = (int)i3;
+            ctx_out->h = make_hj(state[i3], state[i3 + 1], pose_src[0], pose_src[1], pose_src[2]);
+            double zr, zphi;
+            range_bearing(sx, sy, zr, zphi);
+            ctx_out->zr = zr;
+            ctx_out->zphi = zphi;
+        }
+    }
     const bool owns_lm = active && i3 >= r0 && i3 < r1;
     // rank 0 always reports source 0 (zeros when the measurement was dropped) and, when it owns the landmark too or
     // nothing is applied, source 1 as well; any other rank reports source 1 when it owns the landmark
     const bool push0 = rank == 0, push1 = rank == 0 ? (owns_lm || !active) : owns_lm;
     if (!push0 && !push1) return;
+    const long long id[5] = {0, 1, 2, i3, i3 + 1};
+    if (active && threadIdx.x < 32) {
+        if (threadIdx.x == 0) h_s = make_hj(state[i3], state[i3 + 1], pose_src[0], pose_src[1], pose_src[2]);
+        if (threadIdx.x < 5 && id[threadIdx.x] >= r0 && id[threadIdx.x] < r1)
+            for (int j = 0; j < p; ++j) kidx_s[j][threadIdx.x] = Kp[(long long)j * ld + id[threadIdx.x]];
+    }
+    __syncthreads();
     const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (c < ld) {
         double2 w = make_double2(0.0, 0.0);
         if (c < N && active) {
-            const long long id[5] = {0, 1, 2, i3, i3 + 1};
             double sv[5];
+            bool own[5];
 #pragma unroll
             for (int k = 0; k < 5; ++k) {
-                double v = 0.0;
-                if (id[k] >= r0 && id[k] < r1) {
-                    v = sig_local[(id[k] - r0) * ld + c];
-                    for (int j = 0; j < p; ++j) v = apply_factor(v, Kp[(long long)j * ld + id[k]], Wp[(long long)j * ld + c]);
-                }
-                sv[k] = v;
+                own[k] = id[k] >= r0 && id[k] < r1;
+                sv[k] = own[k] ? sig_local[(id[k] - r0) * ld + c] : 0.0;
             }
-            const Hj h = ctx->h;
+#pragma unroll 4
+            for (int j = 0; j < p; ++j) {
+                const double2 wj = Wp[(long long)j * ld + c];
+#pragma unroll
+                for (int k = 0; k < 5; ++k)
+                    if (own[k]) sv[k] = apply_factor(sv[k], kidx_s[j][k], wj);
+            }
+            const Hj h = h_s;
             w = make_double2(h_row0(h, sv[1], sv[2], sv[3], sv[4]), h_row1(h, sv[0], sv[1], sv[2], sv[3], sv[4]));
         }
         // rank 0 owning the landmark: its partial is the whole W (source 0) and source 1 is zero
@@ -710,12 +761,13 @@ int correct(ekf_sharded* h, bool use_cmd, bool stale_pose, int lm, double sx, do
     const int p = h->pending;
     if (h->push) {
         Shard& s = h->sh[0];
-        k_sh_ctx_h<<<1, 32, 0, h->stream>>>(s.state, stale_pose ? s.pose0 : s.state, use_cmd ? s.cmd : nullptr, lm, sx, sy, s.ctx);
         CU(launch_pdl(k_sh_wpart_push, dim3(gl), dim3(256), 0, h->stream, (const double*)s.sig, h->ld, s.r0, s.r1, h->N, h->rank,
-                      (const Ctx*)s.ctx, (const double2*)s.K2, (const double2*)s.W2, p, h->xp, h->gen, h->d_done2));
+                      (const double*)s.state, (const double*)(stale_pose ? s.pose0 : s.state),
+                      (const UpdateCmd*)(use_cmd ? s.cmd : nullptr), lm, sx, sy, s.ctx, (const double2*)s.K2,
+                      (const double2*)s.W2, p, h->xp, h->gen, h->d_done2));
         CU(launch_pdl(k_sh_gain_state_push, dim3(gl), dim3(256), 0, h->stream, (const unsigned char*)h->xlocal, p, h->gen,
                       s.W2 + (long long)p * h->ld, s.K2 + (long long)p * h->ld, s.state, (const Ctx*)s.ctx, h->N, h->ld));
-        h->launches += 3;
+        h->launches += 2;
         h->pending += 1;
         if (!use_cmd && h->pending == kMaxPending) return flush(h, kMaxPending, false);
         return 0;
@@ -938,7 +990,8 @@ int ekf_sharded_predict(ekf_sharded* h, double dtheta, double dx) {
         if (rc) return rc;
     }
     for (auto& s : h->sh) {
-        k_sh_motion<<<1, 32, 0, h->stream>>>(s.state, s.rank == 0 ? s.sig : nullptr, h->ld, dtheta, dx, s.motion);
+        k_sh_motion<<<1, 32, 0, h->stream>>>(s.state, s.rank == 0 ? s.sig : nullptr, h->ld, dtheta, dx, s.motion, s.K2, s.W2,
+                                             h->pending);
         h->launches++;
         int lr_begin = 0;
         if (s.rank == 0) {
@@ -948,10 +1001,6 @@ int ekf_sharded_predict(ekf_sharded* h, double dtheta, double dx) {
         }
         if (s.rows > lr_begin) {
             k_sh_predict_cols<<<(s.rows - lr_begin + 255) / 256, 256, 0, h->stream>>>(s.sig, h->ld, lr_begin, s.rows, s.motion);
-            h->launches++;
-        }
-        if (h->pending > 0) {  // factors carried across the prediction: A K_j, W_j A^T (ekf_large_delayed.cuh)
-            k_large_predict_factors<<<1, 32, 0, h->stream>>>(s.K2, s.W2, h->ld, h->pending, s.motion);
             h->launches++;
         }
     }

@@ -83,10 +83,16 @@ class ShardedEKF:
         _check(self._L.ekf_sharded_predict(self._h, float(dth), float(dx)))
 
     def measurement(self, sensor_reading, visible_list, known_list=None):
-        xy = np.ascontiguousarray(sensor_reading, dtype=np.float64).reshape(-1)
-        vis = np.ascontiguousarray(visible_list, dtype=np.uint8).reshape(-1)
-        assert xy.size == 2 * self.n and vis.size == self.n
-        _check(self._L.ekf_sharded_measurement(self._h, xy.ctypes.data_as(c_double_p), vis.ctypes.data_as(c_u8_p)))
+        xy, vis = sensor_reading, visible_list
+        if not (isinstance(xy, np.ndarray) and xy.dtype == np.float64 and xy.flags.c_contiguous):
+            xy = np.ascontiguousarray(xy, dtype=np.float64)
+        if not (isinstance(vis, np.ndarray) and vis.dtype == np.uint8 and vis.flags.c_contiguous):
+            vis = np.ascontiguousarray(vis, dtype=np.uint8)
+        if xy.size != 2 * self.n or vis.size != self.n:
+            raise ValueError("measurement() takes 2n readings and n visibility flags")
+        rc = self._L.ekf_sharded_measurement(self._h, xy.ctypes.data, vis.ctypes.data)
+        if rc:
+            _check(rc)
 
     def data_association(self, measures, known_list):
         xy = np.ascontiguousarray(measures, dtype=np.float64).reshape(-1)
