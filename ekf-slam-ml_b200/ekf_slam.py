@@ -302,11 +302,19 @@ class PinnedBuffer:
     __del__ = close
 
 
-def _ptr(a):
+def _ptr(a, dtype=None, size=None, what="array"):
+    """Address of a host buffer for the C ABI, which receives no lengths: numpy arrays (and PinnedBuffers) are checked
+    for dtype, contiguity and element count here, because a wrong one would be read past its end or reinterpreted
+    silently.  A raw integer address is passed through (the caller vouches for it)."""
     if isinstance(a, PinnedBuffer):
-        return a.ptr
+        a = a.array
     if isinstance(a, np.ndarray):
-        assert a.flags["C_CONTIGUOUS"]
+        if not a.flags["C_CONTIGUOUS"]:
+            raise ValueError(f"{what}: array must be C-contiguous")
+        if dtype is not None and a.dtype != np.dtype(dtype):
+            raise TypeError(f"{what}: expected dtype {np.dtype(dtype)}, got {a.dtype}")
+        if size is not None and a.size < size:
+            raise ValueError(f"{what}: expected at least {size} elements, got {a.size}")
         return a.ctypes.data
     return int(a)
 
@@ -346,18 +354,33 @@ class EKFBatch:
 
     def step_known(self, twists, xy, visible):
         """prediction + measurement for every filter; host arrays [B,2], [B,2n], [B,n] (uint8)."""
-        check(self._L.ekf_batch_step_known(self._h, _ptr(twists), _ptr(xy), _ptr(visible)))
+        B, n = self.B, self.n
+        check(self._L.ekf_batch_step_known(self._h, _ptr(twists, np.float64, 2 * B, "twists"),
+                                           _ptr(xy, np.float64, 2 * n * B, "xy"), _ptr(visible, np.uint8, n * B, "visible")))
 
     def step_known_sparse(self, twists, offsets, ids, xy, total=None):
         """prediction + measurement from the marker list (visible markers only): twists [B,2], CSR offsets [B+1] int32,
         ids [total] uint8, xy [total,2].  Bit-identical to step_known() on the dense arrays (unlisted slots = 0)."""
-        total = int(offsets[-1]) if total is None else int(total)
-        check(self._L.ekf_batch_step_known_sparse(self._h, _ptr(twists), _ptr(offsets), _ptr(ids), _ptr(xy), total))
+        if isinstance(offsets, (np.ndarray, PinnedBuffer)):
+            off = offsets.array if isinstance(offsets, PinnedBuffer) else offsets
+            last = int(off.reshape(-1)[self.B])
+            if total is not None and int(total) != last:
+                raise ValueError(f"total = {total} does not match offsets[B] = {last}")
+            total = last
+        elif total is None:
+            raise ValueError("total is required when offsets is a raw address")
+        total = int(total)
+        check(self._L.ekf_batch_step_known_sparse(self._h, _ptr(twists, np.float64, 2 * self.B, "twists"),
+                                                  _ptr(offsets, np.int32, self.B + 1, "offsets"),
+                                                  _ptr(ids, np.uint8, total, "ids"), _ptr(xy, np.float64, 2 * total, "xy"),
+                                                  total))
 
     def step_unknown(self, twists, meas, count, m_max, want_assoc=False):
         """prediction + data_association; host arrays [B,2], [B,m_max,2], [B] int32."""
         assoc = np.empty((self.B, m_max), dtype=np.int32) if want_assoc else None
-        check(self._L.ekf_batch_step_unknown(self._h, _ptr(twists), _ptr(meas), _ptr(count), int(m_max),
+        check(self._L.ekf_batch_step_unknown(self._h, _ptr(twists, np.float64, 2 * self.B, "twists"),
+                                             _ptr(meas, np.float64, 2 * int(m_max) * self.B, "meas"),
+                                             _ptr(count, np.int32, self.B, "count"), int(m_max),
                                              assoc.ctypes.data if want_assoc else None))
         return assoc
 
@@ -374,7 +397,7 @@ class EKFBatch:
         return out
 
     def poses_async(self, pinned):
-        check(self._L.ekf_batch_get_poses_async(self._h, _ptr(pinned)))
+        check(self._L.ekf_batch_get_poses_async(self._h, _ptr(pinned, np.float64, 3 * self.B, "poses")))
 
     def states(self):
         out = np.empty((self.B, self.N))

@@ -15,6 +15,8 @@
 #include <iostream>
 #include <random>
 #include <sstream>
+#include <pthread.h>
+#include <sched.h>
 #include <thread>
 #include <vector>
 
@@ -240,6 +242,19 @@ double ref_bench_known(int n, int n_filters, int steps, const double* twists, co
     std::vector<std::thread> th;
     for (int f = 0; f < n_filters; ++f) {
         th.emplace_back([&, f]() {
+            // one filter per host core, pinned: thread f on the f-th CPU of the allowed set
+            cpu_set_t allowed;
+            if (sched_getaffinity(0, sizeof(allowed), &allowed) == 0) {
+                int seen = 0, target = f % CPU_COUNT(&allowed);
+                for (int c = 0; c < CPU_SETSIZE; ++c)
+                    if (CPU_ISSET(c, &allowed) && seen++ == target) {
+                        cpu_set_t one;
+                        CPU_ZERO(&one);
+                        CPU_SET(c, &one);
+                        pthread_setaffinity_np(pthread_self(), sizeof(one), &one);
+                        break;
+                    }
+            }
             EKF_SLAM& F = filters[f];
             int64_t u = 0;
             mat z = zeros<mat>(2 * n, 1);

@@ -344,6 +344,94 @@ def test_large_map_stream_engine(gpu_pkg):
     assert state_err(f.state, o.state) < TOL and sigma_err(f.sigma, o.sigma) < TOL
 
 
+def test_large_map_cfg4_size(gpu_pkg):
+    """BASELINE cfg4 at its full size (n = 8,192, N = 16,387, Sigma 2.1 GB): 14 corrections through the multi-factor
+    DMMA sweep against the O(N^2) oracle, state and the whole covariance."""
+    n = 8192
+    tg = gpu_pkg.tracegen
+    w = tg.grid_world(128, 64, pitch=0.5, n_slots=n, max_visible=0.7)
+    tr = tg.simulate_known(w, 1, 6, seed=99)
+    f = gpu_pkg.EKF_SLAM(n)
+    o = OracleEKF(n)
+    done = t = 0
+    while done < 10:
+        f.prediction(tuple(tr["twists"][t, 0]))
+        f.measurement(tr["xy"][t, 0], tr["vis"][t, 0])
+        o.prediction(*tr["twists"][t, 0])
+        o.measurement(tr["xy"][t, 0], tr["vis"][t, 0])
+        done += int(tr["vis"][t, 0].sum()) if t else 0
+        t += 1
+    assert f.sweep_count <= 1  # the corrections went through (at most) one sweep so far, the rest is pending
+    assert state_err(f.state, o.state) < TOL
+    sig, ref = f.sigma, o.sigma
+    d = np.sqrt(np.abs(np.diag(ref)))
+    worst = 0.0
+    for i0 in range(0, ref.shape[0], 256):
+        sl = slice(i0, i0 + 256)
+        scale = np.maximum(np.maximum(np.abs(ref[sl]), d[sl, None] * d[None, :]), 1e-300)
+        worst = max(worst, float(np.max(np.abs(sig[sl] - ref[sl]) / scale)))
+    assert worst < TOL, worst
+    # the rows / diagonal accessors used by the parity checks of maps too large to read back whole
+    rows = np.array([0, 2, 3, 4097, 16386], dtype=np.int64)
+    assert np.array_equal(f.sigma_rows(rows), sig[rows]) and np.array_equal(f.sigma_diag, np.diag(sig))
+
+
+def test_update_count_with_one_sweep_per_correction(gpu_pkg):
+    """max_pending = 1 (the reference's schedule): data_association() on the streamed engine must count exactly the
+    corrections it applied and must not sweep for a dropped measurement."""
+    n = 300
+    tg = gpu_pkg.tracegen
+    w = tg.grid_world(20, 15, pitch=0.45, n_slots=n, max_visible=1.0)
+    tr = tg.simulate_known(w, 1, 3, seed=2)
+    f = gpu_pkg.EKF_SLAM(n, engine=gpu_pkg.ENGINE_STREAM)
+    f.set_max_pending(1)
+    o = OracleEKF(n)
+    for obj in (f, o):
+        if obj is f:
+            obj.prediction(tuple(tr["twists"][0, 0]))
+        else:
+            obj.prediction(*tr["twists"][0, 0])
+        obj.measurement(tr["xy"][0, 0], tr["vis"][0, 0])
+    ids = np.flatnonzero(tr["vis"][1, 0])[:4]
+    xy = tr["xy"][1, 0].reshape(-1, 2)[ids]
+    meas = np.concatenate([xy, [[55.0, 55.0]]])  # the last one is far from everything: gated out, no correction
+    kf, ko = np.ones(n, np.uint8), np.ones(n, np.uint8)
+    u0, s0 = f.update_count, f.sweep_count
+    r = f.data_association(meas, kf)
+    a, _, _, _ = o.data_association(meas, ko)
+    applied = int(np.sum(a >= 0))
+    assert np.array_equal(r["assoc"], a) and applied >= 3 and a[-1] == -1
+    assert f.update_count - u0 == applied
+    assert state_err(f.state, o.state) < TOL and sigma_err(f.sigma, o.sigma) < TOL
+
+
+def test_streamed_filter_on_a_second_device(gpu_pkg):
+    """The multi-factor sweep opts in to > 48 KB of shared memory per DEVICE: a filter on device 1 after one on device 0."""
+    if gpu_pkg.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    n = 300
+    tg = gpu_pkg.tracegen
+    w = tg.grid_world(20, 15, pitch=0.45, n_slots=n, max_visible=1.0)
+    tr = tg.simulate_known(w, 1, 4, seed=3)
+    for dev in (0, 1):
+        f = gpu_pkg.EKF_SLAM(n, device=dev, engine=gpu_pkg.ENGINE_STREAM)
+        o = OracleEKF(n)
+        ex, es = _run_known(f, o, tr, check_every=2)
+        assert ex < TOL and es < TOL, (dev, ex, es)
+
+
+def test_batch_wrappers_reject_wrong_buffers(gpu_pkg):
+    bt = gpu_pkg.EKFBatch(8, 20)
+    tw = np.zeros((8, 2))
+    with pytest.raises(TypeError):
+        bt.step_known(tw, np.zeros((8, 40)), np.zeros((8, 20), np.int64))  # visible must be uint8
+    with pytest.raises(ValueError):
+        bt.step_known(tw, np.zeros((8, 20)), np.zeros((8, 20), np.uint8))  # xy too short
+    with pytest.raises(ValueError):
+        bt.step_known_sparse(tw, np.zeros(9, np.int32), np.zeros(0, np.uint8), np.zeros((0, 2)), total=5)
+    bt.close()
+
+
 def test_invalid_arguments_do_not_crash(gpu_pkg):
     with pytest.raises(gpu_pkg.EkfError):
         gpu_pkg.EKF_SLAM(0)
