@@ -426,7 +426,10 @@ def laser_leg(pkg, device, n_scans=8192):
         scans.append(sim.laser_scan(360))
     scans = np.ascontiguousarray(np.concatenate(scans, axis=0))
     cf = pkg.CircleFitting(device=device, max_scans=n_scans, max_circles=16)
+    ref_centers, ref_counts = cf.run_batch(scans)  # every cluster fitted (circleRegression on all of them)
+    cf.set_centres_only(True)                      # approxCirclePositions(): accepted centres only
     centers, counts = cf.run_batch(scans)          # warm-up through the host path
+    same = bool(np.array_equal(counts, ref_counts) and np.array_equal(np.nan_to_num(centers), np.nan_to_num(ref_centers)))
     t0 = time.perf_counter()
     reps = 5
     for _ in range(reps):
@@ -443,7 +446,9 @@ def laser_leg(pkg, device, n_scans=8192):
     pkg.circle_fitting._check(L.circles_timer_stop(cf._ctx, ctypes.byref(ms)))
     return {"workload": f"{n_scans} scans x 360 beams (float32), default 10-tube world: clustering + circle fit + classification",
             "scans_per_s_device": reps * n_scans / (ms.value * 1e-3), "scans_per_s_e2e": e2e,
-            "circles_per_scan": float(counts.mean()), "kernel": "k_circles_scan<float>", "gpu_launches": reps}
+            "circles_per_scan": float(counts.mean()), "kernel": "k_circles_scan<float>", "gpu_launches": reps,
+            "mode": "approxCirclePositions (accepted centres only; clusters failing the inscribed-angle test skip the fit)",
+            "centres_identical_to_full_fit": same}
 
 
 
@@ -589,6 +594,7 @@ def scan_to_map_leg(pkg, device, B=8192, steps=12):
     tg = pkg.tracegen
     s = tg.simulate_scans(tg.default_world(N_SLOTS), B, steps + 3, seed=21)
     cf = pkg.CircleFitting(device=device, max_scans=B, max_circles=16)
+    cf.set_centres_only(True)
     bt = pkg.EKFBatch(B, N_SLOTS, device=device)
     M = 16
     total_scans = 0
@@ -844,28 +850,32 @@ def run_ours(args):
         dist.all_reduce(e_t, op=dist.ReduceOp.SUM)
     err = e_t.cpu().numpy()
 
-    # ---- roofline of the dominant kernel (ekf_fused_sym_kernel<20>)
+    # ---- roofline of the dominant kernel (ekf_fused_tile_kernel<false>: the only kernel inside the timed region)
     step_bytes = B * (2.0 * 8 * N * N)                      # dense Sigma in + out, once per filter and step
     conv_bytes = 16.0 * N * N * upd_launch                  # 16 N^2 per measurement-update
-    stair = 16 * 43 + 16 * 27 + 11 * 11 if N == 43 else None  # stored entries of the symmetric staircase layout
-    stored_bytes = B * (2.0 * 8 * (stair + 1) + 2.0 * 8 * (N + 1) + 16 + 17 * n + 8) if stair else None
+    tiled = (n == 20)
+    # bytes one filter-step really moves: the 9,088-B block (Sigma as 15 DMMA fragments + robot rows + state) in and out,
+    # plus its inputs (twist 16 B, 2n readings, n flags) and the init flag in / out
+    stored_bytes = B * (2.0 * 9088 + 16 + 17 * n + 8) if tiled else None
     roof = {
-        "bound": "hbm", "kernel": "ekf_fused_sym_kernel<20>", "unit": "GB/s", "peak": peak_gbs, "peak_source": peak_src,
+        "bound": "hbm", "kernel": "ekf::tile::ekf_fused_tile_kernel<false>" if tiled else "ekf_fused_sym_kernel<0>",
+        "unit": "GB/s", "peak": peak_gbs, "peak_source": peak_src,
         "achieved": step_bytes / (kern_ms_avg * 1e-3) / 1e9,
         "frac": step_bytes / (kern_ms_avg * 1e-3) / 1e9 / peak_gbs,
         # dram__bytes_read.sum + dram__bytes_write.sum per launch of this kernel at this batch size, from the committed
-        # ncu --set full capture (profiles/r1_prof_fused_sym_raw.csv: 0.698 GB + 0.616 GB); not re-measured here
-        "traffic": 1.314e9 if B == FILTERS_PER_GPU else None,
+        # ncu --set full capture (profiles/r2_prof_fused_tile_raw.csv); not re-measured here
+        "traffic": 1.156e9 if (B == FILTERS_PER_GPU and tiled) else None,
         "algorithmic_bytes_per_launch": step_bytes,
         "stored_bytes_per_launch": stored_bytes,
         "physical_achieved": stored_bytes / (kern_ms_avg * 1e-3) / 1e9 if stored_bytes else None,
         "physical_frac": stored_bytes / (kern_ms_avg * 1e-3) / 1e9 / peak_gbs if stored_bytes else None,
-        "note": "unit = one filter-step (prediction + all of the step's corrections with Sigma resident on chip). "
+        "note": "unit = one filter-step (prediction + all of the step's corrections with Sigma resident in registers). "
                 "algorithmic bytes = 16 N^2 B = one read + one write of the dense Sigma the reference keeps; the kernel "
-                "stores Sigma symmetric (block staircase, 1,241 of 1,849 entries), so the bytes it really moves "
-                "(stored_bytes, physical_*; ncu traffic agrees) are a third fewer. per_update_* uses SURVEY.md's 16 N^2 "
-                "per correction and exceeds 1 because the step's corrections share one pass over Sigma. The kernel is "
-                "bound by shared-memory bandwidth (79 % of the LSU wavefront peak), not by HBM",
+                "stores Sigma symmetric (15 DMMA accumulator fragments of the landmark block + 3 robot rows, 1,092 of "
+                "1,849 entries), so the bytes it really moves (stored_bytes, physical_*; ncu traffic agrees) are 40 % fewer. "
+                "per_update_* uses SURVEY.md's 16 N^2 per correction and exceeds 1 because the step's corrections share "
+                "one pass over Sigma. Next to HBM the kernel is held by the FP64 pipe (DMMA + DFMA, ~60 % busy inside the "
+                "correction loop) with three resident warps per SM sub-partition (168 registers each)",
         "per_update_achieved": conv_bytes / (kern_ms_avg * 1e-3) / 1e9,
         "per_update_frac": conv_bytes / (kern_ms_avg * 1e-3) / 1e9 / peak_gbs,
         "updates_per_launch": upd_launch, "kernel_ms": kern_ms_avg,
@@ -877,16 +887,19 @@ def run_ours(args):
         "config": {"workload": "cfg3: Monte-Carlo batch, 65,536 independent filters x 20 landmark slots per GPU, "
                                "known association (prediction + measurement per step), nurtlesim-shaped circle trajectories, "
                                "20-tube world", "filters_per_gpu": B, "n_landmarks": n, "state_dim": N,
-                   "l2": "inputs larger than L2 (Sigma batch = %.0f MB per step, symmetric storage)" % (B * 8.0 * (stair or N * N) / 1e6),
+                   "l2": "inputs larger than L2 (Sigma + state batch = %.0f MB per step)" % (B * 9088.0 / 1e6 if tiled else B * 8.0 * N * N / 1e6),
                    "updates_per_step_per_gpu": upd_launch},
         "clocks": clocks,
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                "ms_per_step": e2e_ms_step,
-                "input": "marker list (visible markers only: twists [B,2], CSR offsets, ids, xy), pinned host buffers, "
-                         "ekf_batch_step_known_sparse + ekf_batch_get_poses_async per step",
-                "dense_arrays": {"value": dense_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d_dense),
-                                 "ms_per_step": dense_ms,
-                                 "input": "dense [B,2n] readings + [B,n] visible flags (ekf_batch_step_known)"}},
+        # headline end-to-end figure: the argument form of the reference's measurement(mat, vector<bool>, ...) - dense
+        # [B,2n] readings + [B,n] visible flags from pinned host buffers, poses read back every step.  The same step fed
+        # with the fake_sensor message as published (visible markers only) is reported beside it.
+        "e2e": {"value": dense_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d_dense), "d2h_bytes_per_step": int(d2h),
+                "ms_per_step": dense_ms,
+                "input": "dense [B,2n] readings + [B,n] visible flags + twists [B,2], pinned host buffers, "
+                         "ekf_batch_step_known + ekf_batch_get_poses_async per step (PCIe-bound: 23.3 MB per step)",
+                "marker_list": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "ms_per_step": e2e_ms_step,
+                                "input": "marker list (visible markers only: twists [B,2], CSR offsets, ids, xy; built on the "
+                                         "host outside the timed region), ekf_batch_step_known_sparse"}},
         "gpu_launches": int(launches),
         "roofline": roof,
         "pose_rmse": {"x": float(np.sqrt(err[0] / err[3])), "y": float(np.sqrt(err[1] / err[3])),

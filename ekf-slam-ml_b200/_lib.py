@@ -45,6 +45,7 @@ SIGNATURES = {
     "ekf_get_landmarks": (ctypes.c_int, [ctypes.c_void_p, c_double_p]),
     "ekf_get_state": (ctypes.c_int, [ctypes.c_void_p, c_double_p]),
     "ekf_set_state": (ctypes.c_int, [ctypes.c_void_p, c_double_p]),
+    "ekf_association_log_open": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p]),
     "ekf_get_sigma": (ctypes.c_int, [ctypes.c_void_p, c_double_p, ctypes.c_int64]),
     "ekf_get_sigma_rows": (ctypes.c_int, [ctypes.c_void_p, c_i64_p, ctypes.c_int, c_double_p, ctypes.c_int64]),
     "ekf_get_sigma_diag": (ctypes.c_int, [ctypes.c_void_p, c_double_p]),
@@ -110,6 +111,7 @@ SIGNATURES = {
     "circles_last_clusters": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, c_i32_p, c_i32_p, c_double_p, c_u8_p,
                                              c_double_p]),
     "circles_fit_clusters": (ctypes.c_int, [ctypes.c_void_p, c_double_p, c_i32_p, ctypes.c_int, c_double_p, c_u8_p]),
+    "circles_set_centres_only": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     "circles_sync": (ctypes.c_int, [ctypes.c_void_p]),
     "circles_timer_start": (ctypes.c_int, [ctypes.c_void_p]),
     "circles_timer_stop": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_float)]),

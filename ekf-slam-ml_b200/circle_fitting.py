@@ -40,6 +40,11 @@ class CircleFitting:
             self._ctx, self._n_beams = h, int(n_beams)
 
     # ---- batched GPU entry points
+    def set_centres_only(self, on=True):
+        """Batched runs then return exactly what approxCirclePositions() returns and skip the fit of clusters that fail
+        the inscribed-angle test (wall segments); accepted centres are unchanged."""
+        _check(self._L.circles_set_centres_only(self._ctx, 1 if on else 0))
+
     def run_batch(self, ranges):
         """ranges [B, n_beams] float32 (LaserScan wire format) or float64 -> (centers [B,max_circles,2], counts [B])."""
         r = np.ascontiguousarray(ranges)

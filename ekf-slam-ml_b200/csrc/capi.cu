@@ -249,6 +249,8 @@ __global__ void k_pose_error(const double* state, long long B, int st_stride, co
 
 // ======================================================================================= handles
 struct ekf_filter {
+    FILE* assoc_log = nullptr;     // ekf_association_log_open(): one line per associated measurement
+    uint64_t assoc_calls = 0;      // data_association() calls so far (the log's first column)
     int n = 0, N = 0, device = 0, engine = 0;
     cudaStream_t stream = nullptr;
     uint64_t launches = 0;
@@ -302,6 +304,8 @@ namespace {
 
 int free_filter(ekf_filter* h) {
     if (!h) return EKF_OK;
+    if (h->assoc_log) fclose(h->assoc_log);
+    h->assoc_log = nullptr;
     DeviceGuard g(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     cudaFree(h->d_sigma);
@@ -751,6 +755,27 @@ int ekf_data_association(ekf_filter* h, const double* xy, int m, uint8_t* known,
     } else {
         for (int i = known_count; i < *o_kc && i < n; ++i) known[i] = 1;
     }
+    if (h->assoc_log) {  // the structured counterpart of the reference's print stream (ekf_slam.cpp:290-329)
+        for (int j = 0; j < m; ++j)
+            fprintf(h->assoc_log, "%llu,%d,%.17g,%.17g,%d,%.17g,%.17g,%d\n", (unsigned long long)h->assoc_calls, j, xy[2 * j],
+                    xy[2 * j + 1], (int)o_assoc[j], o_dmin[j], o_second[j], (int)o_created[j]);
+        fflush(h->assoc_log);
+    }
+    h->assoc_calls += 1;
+    return EKF_OK;
+}
+
+// Association log: a CSV file with one line per measurement handed to data_association(),
+//   call,index,x,y,landmark (-1 = dropped),min_distance,runner_up,created
+// (what the reference only prints, ekf_slam.cpp:290-329).  path = NULL closes the log.
+int ekf_association_log_open(ekf_filter* h, const char* path) {
+    if (!h) return fail(EKF_ERR_INVALID, "null handle");
+    if (h->assoc_log) fclose(h->assoc_log);
+    h->assoc_log = nullptr;
+    if (!path) return EKF_OK;
+    h->assoc_log = fopen(path, "w");
+    if (!h->assoc_log) return fail(EKF_ERR_INVALID, "cannot open %s", path);
+    fprintf(h->assoc_log, "call,index,x,y,landmark,min_distance,runner_up,created\n");
     return EKF_OK;
 }
 

@@ -100,8 +100,25 @@ struct FitResult {
 // Hyper-circle fit + inscribed-angle statistic of one cluster by one warp.  `pt(k)` returns point k.
 // ROWS = design-matrix rows held per lane (cluster size <= 32 * ROWS): tube clusters have 7..40 points, so the
 // common case runs with ROWS = 2 and a sixth of the register-array work of the general (ROWS = 12) instantiation.
+// classifyCircle's statistic: mean inscribed angle over the interior points (:242-263)
+template <class Fetch>
+__device__ __forceinline__ double warp_mean_inscribed_angle(Fetch pt, const int n, const int lane) {
+    const double2 p1 = pt(0), p2 = pt(n - 1);
+    double sa = 0.0;
+    for (int k = 1 + lane; k < n - 1; k += 32) {
+        const double2 p = pt(k);
+        const double ax = p1.x - p.x, ay = p1.y - p.y, bx = p2.x - p.x, by = p2.y - p.y;
+        const double top = __dadd_rn(__dmul_rn(ax, bx), __dmul_rn(ay, by));
+        const double bot = __dmul_rn(sqrt(__dadd_rn(__dmul_rn(ax, ax), __dmul_rn(ay, ay))),
+                                     sqrt(__dadd_rn(__dmul_rn(bx, bx), __dmul_rn(by, by))));
+        sa += acos(top / bot);
+    }
+    return warp_sum(sa) / (double)(n - 2);
+}
+__device__ __forceinline__ bool angle_in_circle_range(double mean_angle) { return mean_angle > 1.5708 && mean_angle < 2.3562; }
+
 template <int ROWS, class Fetch>
-__device__ __forceinline__ FitResult warp_circle_fit_rows(Fetch pt, const int n, const int lane) {
+__device__ __forceinline__ FitResult warp_circle_fit_rows(Fetch pt, const int n, const int lane, const double mean_angle) {
     constexpr int kRows = ROWS;
     double a0[kRows], a1[kRows], a2[kRows], a3[kRows];
     // means (circle_fitting.cpp:112-120)
@@ -285,26 +302,28 @@ __device__ __forceinline__ FitResult warp_circle_fit_rows(Fetch pt, const int n,
     res.cy = cb + ym;
     res.r = sqrt(r2);
 
-    // classifyCircle: mean inscribed angle over the interior points (:242-263)
-    const double2 p1 = pt(0), p2 = pt(n - 1);
-    double sa = 0.0;
-    for (int k = 1 + lane; k < n - 1; k += 32) {
-        const double2 p = pt(k);
-        const double ax = p1.x - p.x, ay = p1.y - p.y, bx = p2.x - p.x, by = p2.y - p.y;
-        const double top = __dadd_rn(__dmul_rn(ax, bx), __dmul_rn(ay, by));
-        const double bot = __dmul_rn(sqrt(__dadd_rn(__dmul_rn(ax, ax), __dmul_rn(ay, ay))),
-                                     sqrt(__dadd_rn(__dmul_rn(bx, bx), __dmul_rn(by, by))));
-        sa += acos(top / bot);
-    }
-    res.mean_angle = warp_sum(sa) / (double)(n - 2);
+    res.mean_angle = mean_angle;
     return res;
 }
 
+// centres_only: approxCirclePositions() returns the ACCEPTED centres, and a cluster is accepted only if its mean
+// inscribed angle is in range AND its fitted radius is small (:264-271).  The angle statistic does not depend on the
+// fit, so it goes first, and a cluster that fails it (every wall segment: a straight run of 50-300 beams whose angle
+// is ~pi) skips the SVD fit altogether; what approxCirclePositions() returns is unchanged.  With centres_only = false
+// every cluster is fitted (circleRegression() / the per-cluster seams).
 template <class Fetch>
-__device__ __forceinline__ FitResult warp_circle_fit(Fetch pt, const int n, const int lane) {
-    if (n <= 64) return warp_circle_fit_rows<2>(pt, n, lane);   // warp-uniform branch
-    if (n <= 128) return warp_circle_fit_rows<4>(pt, n, lane);
-    return warp_circle_fit_rows<kRows>(pt, n, lane);
+__device__ __forceinline__ FitResult warp_circle_fit(Fetch pt, const int n, const int lane, const bool centres_only = false) {
+    const double mean_angle = warp_mean_inscribed_angle(pt, n, lane);
+    if (centres_only && !angle_in_circle_range(mean_angle)) {  // warp-uniform
+        FitResult res;
+        res.cx = res.cy = res.r = nan("");
+        res.mean_angle = mean_angle;
+        res.fallback = 0;
+        return res;
+    }
+    if (n <= 64) return warp_circle_fit_rows<2>(pt, n, lane, mean_angle);   // warp-uniform branch
+    if (n <= 128) return warp_circle_fit_rows<4>(pt, n, lane, mean_angle);
+    return warp_circle_fit_rows<kRows>(pt, n, lane, mean_angle);
 }
 
 __device__ __forceinline__ bool is_circle(const FitResult& f) {
@@ -319,6 +338,7 @@ struct ScanOut {
     double* xy;           // [B][n_beams][2]       cartesian points (device cos/sin), for the clustering seam
     double* centers;      // [B][max_c][2]
     int32_t* counts;      // [B]
+    int centres_only;     // 1: only centers / counts are needed (clusters failing the angle test are not fitted)
 };
 
 template <typename T>
@@ -346,7 +366,7 @@ __global__ void __launch_bounds__(kCtaThreads, CIRC_MIN_CTAS)
             sincos(ekf::normalize_angle((double)i * resol), &s, &c);
         }
         xy[i] = make_double2(v * c, v * s);
-        if (out.xy) {
+        if (out.xy && !out.centres_only) {
             out.xy[(b * n_beams + i) * 2] = v * c;
             out.xy[(b * n_beams + i) * 2 + 1] = v * s;
         }
@@ -401,7 +421,7 @@ __global__ void __launch_bounds__(kCtaThreads, CIRC_MIN_CTAS)
     for (int c = warp; c < ncl; c += kCtaThreads / 32) {
         const Segs sg = seg[c];
         auto fetch = [&](int k) -> double2 { return xy[k < sg.l1 ? sg.s1 + k : sg.s2 + (k - sg.l1)]; };
-        const FitResult f = warp_circle_fit(fetch, sg.l1 + sg.l2, lane);
+        const FitResult f = warp_circle_fit(fetch, sg.l1 + sg.l2, lane, out.centres_only != 0);
         if (lane == 0) {
             res[c][0] = f.cx;
             res[c][1] = f.cy;
@@ -707,6 +727,15 @@ int circles_timer_stop(circles_ctx* c, float* ms_out) {
     CCU(cudaEventElapsedTime(ms_out, c->t0, c->t1));
     return 0;
 }
+// 1: runs return only what approxCirclePositions() returns (accepted centres + counts); clusters that fail the
+// inscribed-angle test are not fitted and circles_last_clusters() reports NaN for them.  0 (default): every cluster is
+// fitted, as circleRegression() does.  The accepted centres are identical in both modes.
+int circles_set_centres_only(circles_ctx* c, int on) {
+    if (!c) return circ::fail(-1, "null handle");
+    c->o.centres_only = on ? 1 : 0;
+    return 0;
+}
+
 int circles_launch_count(circles_ctx* c, uint64_t* out) {
     if (!c || !out) return circ::fail(-1, "null argument");
     *out = c->launches;

@@ -203,6 +203,11 @@ class EKF_SLAM:
         assert v.shape == (self.N, self.N)
         check(self._L.ekf_set_sigma(self._h, v.ctypes.data_as(c_double_p), self.N))
 
+    def association_log(self, path):
+        """CSV log of every data_association() decision from now on (None closes it): call, index, x, y, landmark
+        (-1 = dropped), min_distance, runner_up, created - what the reference only prints (ekf_slam.cpp:290-329)."""
+        check(self._L.ekf_association_log_open(self._h, None if path is None else str(path).encode()))
+
     def sigma_rows(self, rows):
         """Selected rows of the covariance, shape [len(rows), N] (maps too large to read back whole)."""
         rows = np.ascontiguousarray(rows, dtype=np.int64)

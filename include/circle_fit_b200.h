@@ -51,6 +51,12 @@ int circles_last_clusters(circles_ctx* c, int64_t scan, int32_t* n_clusters, int
 int circles_fit_clusters(circles_ctx* c, const double* flat_xy, const int32_t* sizes, int n_clusters, double* cxr,
                          uint8_t* flags);
 
+/* on != 0: subsequent runs produce only what approxCirclePositions() returns (accepted centres and counts).  A
+ * cluster is accepted iff its mean inscribed angle is in range AND its fitted radius is < 0.2 (:264-271); the angle
+ * does not depend on the fit, so clusters failing it (the wall segments) skip the SVD fit.  Accepted centres are
+ * identical in both modes; circles_last_clusters() then reports NaN for unfitted clusters.  Default: off. */
+int circles_set_centres_only(circles_ctx* c, int on);
+
 int circles_sync(circles_ctx* c);
 int circles_timer_start(circles_ctx* c);
 int circles_timer_stop(circles_ctx* c, float* ms_out);

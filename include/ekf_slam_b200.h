@@ -85,6 +85,10 @@ int ekf_get_landmarks(ekf_filter* h, double* out);
 /* full state / covariance access (parity dumps, checkpoint / resume; no reference counterpart) */
 int ekf_get_state(ekf_filter* h, double* out);
 int ekf_set_state(ekf_filter* h, const double* in);
+/* Per-step association log (the reference only prints these decisions, ekf_slam.cpp:290-329): from now on every
+ * ekf_data_association() call appends one CSV line per measurement - call,index,x,y,landmark (-1 = dropped),
+ * min_distance,runner_up,created - to `path`; NULL closes the log. */
+int ekf_association_log_open(ekf_filter* h, const char* path);
 int ekf_get_sigma(ekf_filter* h, double* out, int64_t ld);
 /* `count` selected rows (N doubles each, row stride ld in `out`) and the diagonal (N doubles): for parity checks of
  * maps whose whole covariance is too large to pull to the host */

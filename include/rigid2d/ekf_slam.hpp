@@ -125,6 +125,11 @@ class EKF_SLAM {
     // not in the reference: last C-ABI status (0 = ok) and the association log of the last data_association()
     int last_status() const { return status_; }
     const std::vector<int32_t>& last_association() const { return last_assoc_; }
+    // not in the reference: CSV log of every association decision (ekf_slam_b200.h); nullptr closes it
+    void set_association_log(const char* path) {
+        status_ = ekf_association_log_open(h_, path);
+        report("ekf_association_log_open");
+    }
     ekf_filter* handle() { return h_; }
 
   private:

@@ -166,3 +166,21 @@ def test_golden_scans_from_reference(gpu_pkg):
         nc = int((g["cluster_sizes"][s] > 0).sum())
         assert d["n"] == nc and [len(i) for i in d["ids"]] == list(g["cluster_sizes"][s, :nc])
         assert list(d["is_circle"]) == list(g["cluster_is_circle"][s, :nc].astype(bool))
+
+
+def test_centres_only_mode_returns_the_same_centres(gpu_pkg):
+    """approxCirclePositions() needs only the accepted centres: skipping the fit of clusters that fail the inscribed-
+    angle test must not change them."""
+    tg = gpu_pkg.tracegen
+    sim = tg.TubeWorldSim(tg.default_world(), 256, seed=13)
+    for _ in range(21):
+        sim.step_tick()
+    scans = np.ascontiguousarray(sim.laser_scan(360))
+    cf = gpu_pkg.CircleFitting(max_scans=256, max_circles=16)
+    c_all, n_all = cf.run_batch(scans)
+    cf.set_centres_only(True)
+    c_fast, n_fast = cf.run_batch(scans)
+    assert np.array_equal(n_all, n_fast) and int(n_all.sum()) > 256
+    for b in range(256):
+        k = min(int(n_all[b]), 16)
+        assert np.array_equal(c_all[b, :k], c_fast[b, :k])

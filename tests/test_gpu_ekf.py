@@ -420,6 +420,33 @@ def test_streamed_filter_on_a_second_device(gpu_pkg):
         assert ex < TOL and es < TOL, (dev, ex, es)
 
 
+def test_association_log(gpu_pkg, tmp_path):
+    """The per-call association record the reference only prints: one CSV line per measurement."""
+    tg = gpu_pkg.tracegen
+    tu = tg.simulate_unknown(tg.default_world(20), 1, 12, seed=4)
+    f = gpu_pkg.EKF_SLAM(20)
+    o = OracleEKF(20)
+    log = tmp_path / "assoc.csv"
+    f.association_log(log)
+    kf, ko = np.zeros(20, np.uint8), np.zeros(20, np.uint8)
+    expect = []
+    for t in range(12):
+        m = int(tu["count"][t, 0])
+        f.prediction(tuple(tu["twists"][t, 0]))
+        o.prediction(*tu["twists"][t, 0])
+        if m:
+            f.data_association(tu["meas"][t, 0, :m], kf)
+            a, dmin, sec, cr = o.data_association(tu["meas"][t, 0, :m], ko)
+            expect += [(j, int(a[j]), float(dmin[j]), int(cr[j])) for j in range(m)]
+    f.association_log(None)
+    rows = np.genfromtxt(log, delimiter=",", names=True)
+    assert len(rows) == len(expect) > 20
+    assert [int(v) for v in rows["index"]] == [e[0] for e in expect]
+    assert [int(v) for v in rows["landmark"]] == [e[1] for e in expect]
+    assert [int(v) for v in rows["created"]] == [e[3] for e in expect]
+    np.testing.assert_allclose(rows["min_distance"], [e[2] for e in expect], rtol=1e-7, atol=1e-9)
+
+
 def test_batch_wrappers_reject_wrong_buffers(gpu_pkg):
     bt = gpu_pkg.EKFBatch(8, 20)
     tw = np.zeros((8, 2))
