@@ -105,6 +105,7 @@ class CircleFitting:
                                             cxr.ctypes.data_as(c_double_p), flags.ctypes.data_as(c_u8_p)))
         self.r_cluster.extend(float(v) for v in cxr[:, 2])
         self._flags = [bool(f & 1) for f in flags]
+        self._last_flags_raw = flags  # bit0 = circle, bit1 = eigenvalue fallback
         self._last_cxr = cxr
         return [Vector2D(cxr[i, 0], cxr[i, 1]) for i in range(k)]
 

@@ -120,6 +120,27 @@ def main():
     np.savez_compressed(os.path.join(GOLD, "circles_scans.npz"), ranges=scans, centers=centers, counts=counts,
                         cluster_sizes=np.array(cl_sizes), cluster_cxr=np.array(cl_cxr), cluster_is_circle=np.array(cl_flag))
 
+    # ---- eigenvalue fallback (circle_fitting.cpp:187-197): clusters in coordinates so large that no eigenvalue of
+    # Q lies in (0, 1000); the reference then takes eig_gen's index 0, which LAPACK's dgeev makes the negative one
+    rng = np.random.default_rng(20261018)
+    fb_clusters, fb_sizes = [], []
+    for _ in range(160):
+        npts = int(rng.integers(7, 40))
+        R = rng.uniform(500, 30000)
+        cx, cy = rng.uniform(-5e4, 5e4, 2)
+        a0, span = rng.uniform(0, 2 * np.pi), rng.uniform(0.3, 2.5)
+        t = a0 + np.linspace(0, span, npts)
+        fb_clusters.append(np.stack([cx + R * np.cos(t) + rng.normal(0, 0.05 * R, npts),
+                                     cy + R * np.sin(t) + rng.normal(0, 0.05 * R, npts)], 1))
+        fb_sizes.append(npts)
+    fb_flat = np.ascontiguousarray(np.concatenate(fb_clusters))
+    fb_sizes = np.array(fb_sizes, dtype=np.int32)
+    fb_cxr = np.zeros((len(fb_sizes), 3))
+    fb_isc = np.zeros(len(fb_sizes), np.uint8)
+    L.ref_fit_clusters(fb_flat.ctypes.data_as(dp), fb_sizes.ctypes.data_as(ctypes.POINTER(ctypes.c_int)), len(fb_sizes),
+                       fb_cxr.ctypes.data_as(dp), fb_isc.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)))
+    np.savez(os.path.join(GOLD, "circles_fallback.npz"), flat_xy=fb_flat, sizes=fb_sizes, cxr=fb_cxr, is_circle=fb_isc)
+
     # ---- helpers on the path
     rng = np.random.default_rng(5)
     ang = np.concatenate([rng.uniform(-30, 30, 200), [0.0, np.pi, -np.pi, 2 * np.pi, 7.0, -7.0, 100.0]])

@@ -184,3 +184,27 @@ def test_centres_only_mode_returns_the_same_centres(gpu_pkg):
     for b in range(256):
         k = min(int(n_all[b]), 16)
         assert np.array_equal(c_all[b, :k], c_fast[b, :k])
+
+
+def test_eigenvalue_fallback_matches_the_reference_build(gpu_pkg):
+    """circle_fitting.cpp:187-197: with no eigenvalue in (0, 1000) the reference takes eig_gen's index 0.  For this
+    matrix family LAPACK returns the (single) negative eigenvalue first, so that is the defined fallback here; the
+    fixture holds 160 large-coordinate clusters fitted by the reference build (scripts/make_golden.py)."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "circles_fallback.npz"))
+    sizes, flat, ref = g["sizes"], g["flat_xy"], g["cxr"]
+    cf = gpu_pkg.CircleFitting()
+    from ekf_slam_ml_b200 import Vector2D
+    clusters, p = [], 0
+    for k in sizes:
+        clusters.append([Vector2D(float(x), float(y)) for x, y in flat[p:p + k]])
+        p += k
+    cf.set_xy_cluster(clusters)
+    pos = cf.circleRegression()
+    r = cf.get_r_cluster()
+    assert all(bool(f) for f in (cf._last_flags_raw & 2 != 0)), "every fixture cluster takes the fallback"
+    worst = 0.0
+    for c in range(len(sizes)):
+        scale = max(abs(ref[c, 0]), abs(ref[c, 1]), abs(ref[c, 2]))
+        worst = max(worst, abs(pos[c].x - ref[c, 0]) / scale, abs(pos[c].y - ref[c, 1]) / scale, abs(r[c] - ref[c, 2]) / scale)
+    assert worst < 1e-8, worst
