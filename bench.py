@@ -328,7 +328,7 @@ def large_map_leg(pkg, device, n_lm, timed_updates, peak_gbs, want_cpu):
                     f"prediction + gain + streamed rank-2 sweep per correction",
         "value": 1e3 / ms_upd, "unit": UNIT, "updates_timed": done, "ms_per_update": ms_upd,
         "gpu_launches": int(launches),
-        "roofline": {"bound": "hbm", "kernel": "k_large_sweep_tma<P> / k_large_sweep_p<P> (time per sweep = whole step incl. predict + gains)",
+        "roofline": {"bound": "hbm", "kernel": "k_large_sweep_mma<P> (time per sweep = whole step incl. predict + gains)",
                      "achieved": alg_bytes * n_sweeps / (sweep_ms_total * 1e-3) / 1e9, "peak": peak_gbs, "unit": "GB/s",
                      "frac": alg_bytes * n_sweeps / (sweep_ms_total * 1e-3) / 1e9 / peak_gbs,
                      # ncu capture profiles/r1_prof_sweep_tma_raw.csv (P = 12): 2.220 GB read + 2.096 GB written per launch
@@ -396,11 +396,12 @@ def sharded_map_leg(pkg, dist, local, n_lm, timed_updates, peak_gbs):
     per_gpu_bytes = 16.0 * N * N / world
     out = {
         "workload": f"cfg5: single map, n={n_lm} landmarks (N={N}, Sigma {8.0 * N * N / 1e9:.1f} GB) row-block-sharded over "
-                    f"{world} GPUs; per correction: one NCCL all-reduce of W (2N fp64), K = W^T S^-1 formed on every rank, sweep of own rows",
+                    f"{world} GPUs; per correction: exchange of the partial W (2N fp64; {getattr(f, 'exchange', 'nccl all-reduce')}), "
+                    f"K = W^T S^-1 formed on every rank, sweep of own rows",
         "value": 1e3 / ms_upd, "unit": UNIT, "updates_timed": done, "ms_per_update": ms_upd,
         "gpu_launches_rank0": int(f.launch_count - l0), "rows_rank0": list(rows), "w_exchange": getattr(f, "exchange", "nccl all-reduce"),
-        "roofline": {"bound": "hbm", "kernel": "k_large_sweep_p<P> on each rank's rows (time per sweep = whole step incl. "
-                                                "prediction, gains and the NCCL exchanges)",
+        "roofline": {"bound": "hbm", "kernel": "k_large_sweep_mma<P> on each rank's rows (time per sweep = whole step incl. "
+                                                "prediction, gains and the W exchanges)",
                      "achieved": per_gpu_bytes * n_sweeps / (total_ms * 1e-3) / 1e9, "peak": peak_gbs, "unit": "GB/s per GPU",
                      "frac": per_gpu_bytes * n_sweeps / (total_ms * 1e-3) / 1e9 / peak_gbs, "traffic": None,
                      "algorithmic_bytes_per_launch_per_gpu": per_gpu_bytes, "sweeps": n_sweeps,

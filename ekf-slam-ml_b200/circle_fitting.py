@@ -20,6 +20,7 @@ class CircleFitting:
         self._L = _lib.load()
         self.device, self.max_scans, self.max_circles = int(device), int(max_scans), int(max_circles)
         self._ctx, self._n_beams = None, None
+        self._centres_only = False
         self.point_cluster, self.xy_cluster, self.r_cluster = [], [], []
         self._flags = []
         self.MAXC = self._L.circles_max_clusters()
@@ -38,12 +39,16 @@ class CircleFitting:
             h = ctypes.c_void_p()
             _check(self._L.circles_create(self.max_scans, int(n_beams), self.max_circles, self.device, ctypes.byref(h)))
             self._ctx, self._n_beams = h, int(n_beams)
+            if self._centres_only:
+                _check(self._L.circles_set_centres_only(self._ctx, 1))
 
     # ---- batched GPU entry points
     def set_centres_only(self, on=True):
         """Batched runs then return exactly what approxCirclePositions() returns and skip the fit of clusters that fail
         the inscribed-angle test (wall segments); accepted centres are unchanged."""
-        _check(self._L.circles_set_centres_only(self._ctx, 1 if on else 0))
+        self._centres_only = bool(on)  # kept across the lazy (re)creation of the device context
+        if self._ctx is not None:
+            _check(self._L.circles_set_centres_only(self._ctx, 1 if on else 0))
 
     def run_batch(self, ranges):
         """ranges [B, n_beams] float32 (LaserScan wire format) or float64 -> (centers [B,max_circles,2], counts [B])."""

@@ -280,6 +280,11 @@ struct ekf_filter {
     size_t ring_bytes = 0;
     int ring_pos = 0;
     unsigned char* h_out = nullptr;  // pinned output staging
+    // Fused engine: the kernels read their inputs from the pinned ring and leave the pose in h_pose through the
+    // device mapping of that memory (no copy commands on the stream; a step is launch + synchronise).
+    double* h_pose = nullptr;
+    bool pose_host_ok = false;  // h_pose holds the pose of the last enqueued kernel
+    bool external = false;      // ekf_device_pointers() handed the state out: h_pose can no longer be trusted
     size_t h_out_bytes = 0;
     // stream engine scratch
     double2* d_K2 = nullptr;  // [kMaxPending][ld] pending gain factors
@@ -335,6 +340,7 @@ int free_filter(ekf_filter* h) {
         if (h->ring_ev[i]) cudaEventDestroy(h->ring_ev[i]);
     }
     if (h->h_out) cudaFreeHost(h->h_out);
+    if (h->h_pose) cudaFreeHost(h->h_pose);
     if (h->t0) cudaEventDestroy(h->t0);
     if (h->t1) cudaEventDestroy(h->t1);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -409,6 +415,7 @@ FusedParams fused_params(ekf_filter* h, int mode, int m_max) {
     p.second_out = h->d_second;
     p.created_out = h->d_created;
     p.n_updates = h->d_nupd;
+    p.pose_out = h->h_pose;
     p.B = 1;
     p.n = h->n;
     p.m_max = m_max;
@@ -531,6 +538,7 @@ int ekf_create_ex(int n, int device, int engine, ekf_filter** out) {
     CUH(cudaMalloc(&h->d_scalar, sizeof(double)));
     CUH(cudaMemsetAsync(h->d_nupd, 0, sizeof(unsigned long long), h->stream));
     if (engine == EKF_ENGINE_FUSED) {
+        CUH(cudaMallocHost((void**)&h->h_pose, 64));
         k_fused_init<<<1, 256, 0, h->stream>>>(h->d_sigma, h->d_state, h->d_init_flag, 1, h->N, (int)h->sig_elems,
                                                 h->st_stride);
     } else {
@@ -618,11 +626,12 @@ int ekf_predict(ekf_filter* h, double dtheta, double dx) {
         double* tw = reinterpret_cast<double*>(slot);
         tw[0] = dtheta;
         tw[1] = dx;
-        CU(cudaMemcpyAsync(h->d_twist, tw, 2 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-        CU(cudaEventRecord(ev, h->stream));
         FusedParams p = fused_params(h, kDoPredict, 1);
+        p.twists = tw;  // read through the device mapping of the pinned slot
         rc = launch_fused(p, h->stream, h->device);
+        CU(cudaEventRecord(ev, h->stream));
         h->launches += 1;
+        h->pose_host_ok = rc == EKF_OK;
         return rc;
     }
     if (h->pending > 0 && !h->carry_pending) {
@@ -650,12 +659,13 @@ int ekf_measurement(ekf_filter* h, const double* xy, const uint8_t* visible) {
         if (rc) return rc;
         memcpy(slot, xy, sizeof(double) * 2 * n);
         memcpy(slot + sizeof(double) * 2 * n, visible, n);
-        CU(cudaMemcpyAsync(h->d_in, slot, sizeof(double) * 2 * n, cudaMemcpyHostToDevice, h->stream));
-        CU(cudaMemcpyAsync(h->d_flags, slot + sizeof(double) * 2 * n, n, cudaMemcpyHostToDevice, h->stream));
-        CU(cudaEventRecord(ev, h->stream));
         FusedParams p = fused_params(h, kDoMeasurement, 1);
+        p.xy = reinterpret_cast<const double*>(slot);
+        p.vis = slot + sizeof(double) * 2 * n;
         rc = launch_fused(p, h->stream, h->device);
+        CU(cudaEventRecord(ev, h->stream));
         h->launches += 1;
+        h->pose_host_ok = rc == EKF_OK;
         return rc;
     }
     // stream engine: the host sequences one (gain, sweep) pair per visible landmark; readings travel as kernel
@@ -705,16 +715,34 @@ int ekf_data_association(ekf_filter* h, const double* xy, int m, uint8_t* known,
     while (known_count < n && known[known_count]) ++known_count;  // leading-true prefix, ekf_slam.cpp:281-288
     slot_i[0] = m;
     slot_i[1] = known_count;
-    CU(cudaMemcpyAsync(h->d_in, slot, sizeof(double) * 2 * m, cudaMemcpyHostToDevice, h->stream));
-    CU(cudaMemcpyAsync(h->d_flags, slot + sizeof(double) * 2 * m, n, cudaMemcpyHostToDevice, h->stream));
+    // outputs: one pinned staging area, one synchronisation
+    unsigned char* o = h->h_out;
+    int32_t* o_assoc = reinterpret_cast<int32_t*>(o);
+    double* o_dmin = reinterpret_cast<double*>(o + (((size_t)m * 4 + 15) & ~(size_t)15));
+    double* o_second = o_dmin + m;
+    uint8_t* o_created = reinterpret_cast<uint8_t*>(o_second + m);
+    uint8_t* o_known = o_created + ((m + 15) & ~15);
+    int* o_kc = reinterpret_cast<int*>(o_known + ((n + 15) & ~15));
     if (h->engine == EKF_ENGINE_FUSED) {
-        CU(cudaMemcpyAsync(h->d_mcount, slot_i, sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
-        CU(cudaEventRecord(ev, h->stream));
+        // the kernel reads the slot and writes the log straight into the pinned areas (device mapping of both)
         FusedParams p = fused_params(h, kDoAssociation, m);
+        p.xy = reinterpret_cast<const double*>(slot);
+        p.known = slot + sizeof(double) * 2 * m;
+        p.mcount = slot_i;
+        p.assoc_out = o_assoc;
+        p.dmin_out = o_dmin;
+        p.second_out = o_second;
+        p.created_out = o_created;
         rc = launch_fused(p, h->stream, h->device);
+        CU(cudaEventRecord(ev, h->stream));
         h->launches += 1;
+        h->pose_host_ok = rc == EKF_OK;
         if (rc) return rc;
+        CU(cudaStreamSynchronize(h->stream));
+        memcpy(o_known, slot + sizeof(double) * 2 * m, n);
     } else {
+        CU(cudaMemcpyAsync(h->d_in, slot, sizeof(double) * 2 * m, cudaMemcpyHostToDevice, h->stream));
+        CU(cudaMemcpyAsync(h->d_flags, slot + sizeof(double) * 2 * m, n, cudaMemcpyHostToDevice, h->stream));
         CU(cudaMemcpyAsync(h->d_known_count, slot_i + 1, sizeof(int), cudaMemcpyHostToDevice, h->stream));
         CU(cudaEventRecord(ev, h->stream));
         for (int j = 0; j < m; ++j) {
@@ -728,24 +756,13 @@ int ekf_data_association(ekf_filter* h, const double* xy, int m, uint8_t* known,
             rc = stream_flush(h, 1, h->d_cmd);
             if (rc) return rc;
         }
-    }
-    // outputs: one pinned staging area, one synchronisation
-    unsigned char* o = h->h_out;
-    int32_t* o_assoc = reinterpret_cast<int32_t*>(o);
-    double* o_dmin = reinterpret_cast<double*>(o + (((size_t)m * 4 + 15) & ~(size_t)15));
-    double* o_second = o_dmin + m;
-    uint8_t* o_created = reinterpret_cast<uint8_t*>(o_second + m);
-    uint8_t* o_known = o_created + ((m + 15) & ~15);
-    int* o_kc = reinterpret_cast<int*>(o_known + ((n + 15) & ~15));
-    CU(cudaMemcpyAsync(o_assoc, h->d_assoc, sizeof(int32_t) * m, cudaMemcpyDeviceToHost, h->stream));
-    CU(cudaMemcpyAsync(o_dmin, h->d_dmin, sizeof(double) * m, cudaMemcpyDeviceToHost, h->stream));
-    CU(cudaMemcpyAsync(o_second, h->d_second, sizeof(double) * m, cudaMemcpyDeviceToHost, h->stream));
-    CU(cudaMemcpyAsync(o_created, h->d_created, m, cudaMemcpyDeviceToHost, h->stream));
-    if (h->engine == EKF_ENGINE_FUSED)
-        CU(cudaMemcpyAsync(o_known, h->d_flags, n, cudaMemcpyDeviceToHost, h->stream));
-    else
+        CU(cudaMemcpyAsync(o_assoc, h->d_assoc, sizeof(int32_t) * m, cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaMemcpyAsync(o_dmin, h->d_dmin, sizeof(double) * m, cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaMemcpyAsync(o_second, h->d_second, sizeof(double) * m, cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaMemcpyAsync(o_created, h->d_created, m, cudaMemcpyDeviceToHost, h->stream));
         CU(cudaMemcpyAsync(o_kc, h->d_known_count, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-    CU(cudaStreamSynchronize(h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+    }
     if (assoc_out) memcpy(assoc_out, o_assoc, sizeof(int32_t) * m);
     if (dmin_out) memcpy(dmin_out, o_dmin, sizeof(double) * m);
     if (second_out) memcpy(second_out, o_second, sizeof(double) * m);
@@ -804,6 +821,7 @@ int ekf_get_state(ekf_filter* h, double* out) {
 int ekf_set_state(ekf_filter* h, const double* in) {
     if (!h || !in) return fail(EKF_ERR_INVALID, "null argument");
     DeviceGuard g(h->device);
+    h->pose_host_ok = false;
     CU(cudaMemcpyAsync(h->d_state, in, sizeof(double) * h->N, cudaMemcpyHostToDevice, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     return EKF_OK;
@@ -811,6 +829,13 @@ int ekf_set_state(ekf_filter* h, const double* in) {
 int ekf_get_pose(ekf_filter* h, double* out3) {
     if (!h || !out3) return fail(EKF_ERR_INVALID, "null argument");
     DeviceGuard g(h->device);
+    if (h->engine == EKF_ENGINE_FUSED && h->pose_host_ok && !h->external) {
+        CU(cudaStreamSynchronize(h->stream));  // the last kernel left the pose in pinned memory
+        out3[0] = h->h_pose[0];
+        out3[1] = h->h_pose[1];
+        out3[2] = h->h_pose[2];
+        return EKF_OK;
+    }
     CU(cudaMemcpyAsync(out3, h->d_state, 3 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     return EKF_OK;
@@ -926,6 +951,7 @@ int ekf_device_pointers(ekf_filter* h, void** sigma, int64_t* ld, void** state) 
     if (sigma) *sigma = h->d_sigma;
     if (ld) *ld = h->ld;
     if (state) *state = h->d_state;
+    h->external = true;
     return EKF_OK;
 }
 // How many corrections the streamed engine may accumulate before it sweeps Sigma (1..kMaxPending = 14, default 14).  The result

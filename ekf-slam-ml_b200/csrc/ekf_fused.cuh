@@ -33,6 +33,7 @@ struct FusedParams {
     double* second_out;    // [B][m_max] or null
     uint8_t* created_out;  // [B][m_max] or null
     unsigned long long* n_updates;  // running count of landmark corrections, or null
+    double* pose_out;      // [B][3] or null: theta, x, y after the step (single filter: mapped pinned host memory)
     long long B;
     int n;
     int m_max;
@@ -463,6 +464,7 @@ __global__ void __launch_bounds__(32) ekf_fused_kernel(const FusedParams p) {
     __syncwarp();
     fence_proxy_async_smem();
     __syncwarp();
+    if (p.pose_out && lane < 3) p.pose_out[3 * b + lane] = st[lane];
     if (lane == 0) {
         bulk_s2g(g_sig, sig, sig_bytes);
         bulk_s2g(g_st, st, st_bytes);

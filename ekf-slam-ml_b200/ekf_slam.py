@@ -101,6 +101,7 @@ class EKF_SLAM:
         check(self._L.ekf_create_ex(self.n, device, engine, ctypes.byref(h)))
         self._h = h
         self.last_assoc = None
+        self._pose_cache = None
 
     def close(self):
         if getattr(self, "_h", None):
@@ -120,6 +121,7 @@ class EKF_SLAM:
             dth, dx = twist.angular(), twist.linearX()
         else:
             dth, dx = twist
+        self._pose_cache = None
         check(self._L.ekf_predict(self._h, float(dth), float(dx)))
 
     def measurement(self, sensor_reading, visible_list, known_list=None):
@@ -128,6 +130,7 @@ class EKF_SLAM:
         vis = np.ascontiguousarray(visible_list, dtype=np.uint8).reshape(-1)
         if xy.size != 2 * self.n or vis.size != self.n:
             raise ValueError("sensor_reading must hold 2n values and visible_list n flags")
+        self._pose_cache = None
         check(self._L.ekf_measurement(self._h, xy.ctypes.data_as(c_double_p), vis.ctypes.data_as(c_u8_p)))
 
     def data_association(self, measures, known_list):
@@ -142,6 +145,7 @@ class EKF_SLAM:
         dmin = np.zeros(m)
         second = np.zeros(m)
         created = np.zeros(m, dtype=np.uint8)
+        self._pose_cache = None
         check(self._L.ekf_data_association(self._h, xy.ctypes.data_as(c_double_p), m, known.ctypes.data_as(c_u8_p),
                                            assoc.ctypes.data_as(c_i32_p), dmin.ctypes.data_as(c_double_p),
                                            second.ctypes.data_as(c_double_p), created.ctypes.data_as(c_u8_p)))
@@ -169,9 +173,12 @@ class EKF_SLAM:
 
     # --- seams for parity tests / checkpointing (no reference counterpart; state and sigma are private there)
     def _pose(self):
-        out = np.zeros(3)
-        check(self._L.ekf_get_pose(self._h, out.ctypes.data_as(c_double_p)))
-        return out
+        # x, y and theta are read one after the other (slam.cpp:433-434): one device read serves all three
+        if self._pose_cache is None:
+            out = np.zeros(3)
+            check(self._L.ekf_get_pose(self._h, out.ctypes.data_as(c_double_p)))
+            self._pose_cache = out
+        return self._pose_cache
 
     def calculate_maha_dis(self, measure, ith_tube):
         mx, my = (measure.x, measure.y) if isinstance(measure, Vector2D) else measure
@@ -189,6 +196,7 @@ class EKF_SLAM:
     def state(self, v):
         v = np.ascontiguousarray(v, dtype=np.float64).reshape(-1)
         assert v.size == self.N
+        self._pose_cache = None
         check(self._L.ekf_set_state(self._h, v.ctypes.data_as(c_double_p)))
 
     @property
@@ -274,6 +282,7 @@ class EKF_SLAM:
     def clone(self):
         other = object.__new__(EKF_SLAM)
         other._L, other.n, other.N, other.last_assoc = self._L, self.n, self.N, None
+        other._pose_cache = None
         h = ctypes.c_void_p()
         check(self._L.ekf_clone(self._h, ctypes.byref(h)))
         other._h = h

@@ -69,6 +69,7 @@ class EKF_SLAM {
             release();
             h_ = o.h_;
             status_ = o.status_;
+            pose_ok_ = false;
             o.h_ = nullptr;
         }
         return *this;
@@ -76,6 +77,7 @@ class EKF_SLAM {
     ~EKF_SLAM() { release(); }
 
     void prediction(const rigid2d::Twist2D& twist) {
+        pose_ok_ = false;
         status_ = ekf_predict(h_, twist.angular(), twist.linearX());
         report("ekf_predict");
     }
@@ -88,6 +90,7 @@ class EKF_SLAM {
         std::vector<uint8_t> vis((size_t)n, 0);
         for (int i = 0; i < 2 * n && i < (int)sensor_reading.n_elem; ++i) xy[i] = sensor_reading(i, 0);
         for (int i = 0; i < n && i < (int)visible_list.size(); ++i) vis[i] = visible_list[i] ? 1 : 0;
+        pose_ok_ = false;
         status_ = ekf_measurement(h_, xy.data(), vis.data());
         report("ekf_measurement");
     }
@@ -103,6 +106,7 @@ class EKF_SLAM {
         std::vector<uint8_t> known((size_t)n, 0);
         for (int i = 0; i < n && i < (int)known_list.size(); ++i) known[i] = known_list[i] ? 1 : 0;
         last_assoc_.assign(measures.size(), -1);
+        pose_ok_ = false;
         status_ = ekf_data_association(h_, xy.data(), (int)measures.size(), known.data(), last_assoc_.data(), nullptr,
                                        nullptr, nullptr);
         report("ekf_data_association");
@@ -130,21 +134,31 @@ class EKF_SLAM {
         status_ = ekf_association_log_open(h_, path);
         report("ekf_association_log_open");
     }
-    ekf_filter* handle() { return h_; }
+    ekf_filter* handle() {
+        pose_ok_ = false;  // the caller may change the filter behind this object
+        return h_;
+    }
 
   private:
     ekf_filter* h_ = nullptr;
     int status_ = 0;
     std::vector<int32_t> last_assoc_;
 
+    // The nodes read x, y and theta one after the other (slam.cpp:433-434): one device read serves all three.
+    double pose_[3] = {0.0, 0.0, 0.0};
+    bool pose_ok_ = false;
     double pose(int k) {
-        double p[3] = {0.0, 0.0, 0.0};
-        status_ = ekf_get_pose(h_, p);
-        report("ekf_get_pose");
-        return p[k];
+        if (!pose_ok_) {
+            pose_[0] = pose_[1] = pose_[2] = 0.0;
+            status_ = ekf_get_pose(h_, pose_);
+            report("ekf_get_pose");
+            pose_ok_ = status_ == 0;
+        }
+        return pose_[k];
     }
     void copy_from(const EKF_SLAM& o) {
         h_ = nullptr;
+        pose_ok_ = false;
         status_ = o.h_ ? ekf_clone(o.h_, &h_) : 0;
         report("ekf_clone");
     }
