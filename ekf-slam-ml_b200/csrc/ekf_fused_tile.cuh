@@ -329,8 +329,9 @@ static __device__ __noinline__ Innov make_innov_cold(double mx, double my, doubl
 // (ekf_slam.cpp:217-276), read from the mirrors of the robot rows and of the landmarks' diagonal blocks.
 __device__ __forceinline__ double maha_distance_mirror(const double* __restrict__ robm, const double* __restrict__ dgm,
                                                        const int i, const double* rob6, double mx, double my, double zr,
-                                                       double zphi, double theta, double x, double y) {
+                                                       double zphi, double theta, double x, double y, Hj& h_out) {
     const Hj h = make_hj(mx, my, theta, x, y);
+    h_out = h;
     const int i3 = 3 + 2 * i, i4 = i3 + 1;
     const double c03 = robm[i3], c04 = robm[i4], c13 = robm[kPad + i3], c14 = robm[kPad + i4],
                  c23 = robm[2 * kPad + i3], c24 = robm[2 * kPad + i4];
@@ -351,6 +352,21 @@ __device__ __forceinline__ double maha_distance_mirror(const double* __restrict_
     const double t0 = __dadd_rn(__dmul_rn(v0, pi.i00), __dmul_rn(v1, pi.i10));
     const double t1 = __dadd_rn(__dmul_rn(v0, pi.i01), __dmul_rn(v1, pi.i11));
     return __dadd_rn(__dmul_rn(t0, v0), __dmul_rn(t1, v1));
+}
+
+static __device__ __noinline__ Hj make_hj_cold(double mx, double my, double theta, double x, double y) {
+    return make_hj(mx, my, theta, x, y);
+}
+
+// Order-preserving map of a double onto an unsigned 64-bit key (and back): the association's minimum and runner-up
+// are then four warp-wide REDUX.MIN on the key halves instead of a five-round shuffle tree.
+__device__ __forceinline__ unsigned long long ordered_key(double d) {
+    const long long b = __double_as_longlong(d);
+    return (unsigned long long)(b ^ ((b >> 63) | (long long)0x8000000000000000ull));
+}
+__device__ __forceinline__ double key_value(unsigned hi, unsigned lo) {
+    const long long k = (long long)(((unsigned long long)hi << 32) | lo);
+    return __longlong_as_double(k ^ ((~k >> 63) | (long long)0x8000000000000000ull));
 }
 
 static __device__ __noinline__ void landmark_from_reading_cold(double sx, double sy, double theta, double x, double y,
@@ -678,6 +694,8 @@ __global__ void __launch_bounds__(32, EKF_TILE_MINB) ekf_fused_tile_kernel(const
                 if (known_count > n || known_count < 0) known_count = n;
             }
             const int known_count0 = known_count;
+            constexpr int kHjLd = 24;      // six fields x 24 lanes in the rows of the (unused here) second correction
+            double* const hjm = G3b - 1;
             bool mirrors_stale = true;
             const int g = lane >> 2, t = lane & 3;
             for (int j = 0; j < m; ++j) {
@@ -702,30 +720,41 @@ __global__ void __launch_bounds__(32, EKF_TILE_MINB) ekf_fused_tile_kernel(const
                     __syncwarp();
                     mirrors_stale = false;
                 }
+                TILE_PROF_MARK(8);
                 const double zr = zbuf[2 * j], zphi = zbuf[2 * j + 1];
                 const double theta = st[0], x = st[1], y = st[2];  // live pose (:219-221)
-                double best = INFINITY, second = INFINITY;
-                int best_i = 0x7fffffff;
+                // every known landmark's distance, one lane each; the lane's H_j stays in shared memory because the
+                // update of the chosen landmark needs exactly that one again (same pose, same landmark position)
+                double dist = INFINITY;
                 if (lane < known_count) {
                     const double rob6[6] = {robm[0], robm[1], robm[2], robm[kPad + 1], robm[kPad + 2], robm[2 * kPad + 2]};
-                    double d = maha_distance_mirror(robm, dgm, lane, rob6, st[3 + 2 * lane], st[4 + 2 * lane], zr, zphi,
-                                                    theta, x, y);
-                    if (!(d == d)) d = INFINITY;  // NaN never wins
-                    best = d;
-                    best_i = lane;
+                    Hj hl;
+                    dist = maha_distance_mirror(robm, dgm, lane, rob6, st[3 + 2 * lane], st[4 + 2 * lane], zr, zphi, theta, x,
+                                                y, hl);
+                    if (!(dist == dist)) dist = INFINITY;  // NaN never wins
+                    hjm[lane] = hl.a;
+                    hjm[kHjLd + lane] = hl.b;
+                    hjm[2 * kHjLd + lane] = hl.e;
+                    hjm[3 * kHjLd + lane] = hl.f;
+                    hjm[4 * kHjLd + lane] = hl.zr;
+                    hjm[5 * kHjLd + lane] = hl.zphi;
                 }
-#pragma unroll
-                for (int off = 16; off > 0; off >>= 1) {
-                    const double ob = __shfl_xor_sync(kFull, best, off);
-                    const double os = __shfl_xor_sync(kFull, second, off);
-                    const int oi = __shfl_xor_sync(kFull, best_i, off);
-                    if (better(ob, oi, best, best_i)) {
-                        second = fmin(best, os);
-                        best = ob;
-                        best_i = oi;
-                    } else {
-                        second = fmin(second, ob);
-                    }
+                __syncwarp();
+                TILE_PROF_MARK(9);
+                // minimum with the lowest index on ties (:300-309) and the runner-up
+                double best, second;
+                int best_i;
+                {
+                    const unsigned long long key = ordered_key(dist);
+                    const unsigned hi = (unsigned)(key >> 32), lo = (unsigned)key;
+                    const unsigned mhi = __reduce_min_sync(kFull, hi);
+                    const unsigned mlo = __reduce_min_sync(kFull, hi == mhi ? lo : 0xffffffffu);
+                    best_i = __ffs(__ballot_sync(kFull, hi == mhi && lo == mlo)) - 1;
+                    best = key_value(mhi, mlo);
+                    const bool other = lane != best_i;
+                    const unsigned shi = __reduce_min_sync(kFull, other ? hi : 0xffffffffu);
+                    const unsigned slo = __reduce_min_sync(kFull, other && hi == shi ? lo : 0xffffffffu);
+                    second = key_value(shi, slo);
                 }
                 double min_d = kGateNew;
                 int min_idx = known_count;
@@ -742,6 +771,7 @@ __global__ void __launch_bounds__(32, EKF_TILE_MINB) ekf_fused_tile_kernel(const
                     if (p.second_out) p.second_out[o] = second;
                 }
                 int created = 0;
+                TILE_PROF_MARK(10);
                 if (min_idx == known_count && min_idx < n) {  // :318-327
                     if (lane == 0) {
                         double mx, my;
@@ -757,19 +787,35 @@ __global__ void __launch_bounds__(32, EKF_TILE_MINB) ekf_fused_tile_kernel(const
                     created = 1;
                 }
                 int assoc = -1;
+                TILE_PROF_MARK(11);
                 if (min_d < kGateUpdate) {  // :330
-                    const double th_l = st[0], x_l = st[1], y_l = st[2];  // live pose (:331-333)
-                    const Hj h = make_hj(st[3 + 2 * min_idx], st[4 + 2 * min_idx], th_l, x_l, y_l);
+                    // H_j at the live pose (:331-346): what the chosen landmark's lane already evaluated for its
+                    // distance, unless the landmark was created just now
+                    Hj h;
+                    if (created) {
+                        h = make_hj_cold(st[3 + 2 * min_idx], st[4 + 2 * min_idx], st[0], st[1], st[2]);
+                    } else {
+                        h.a = hjm[min_idx];
+                        h.b = hjm[kHjLd + min_idx];
+                        h.e = hjm[2 * kHjLd + min_idx];
+                        h.f = hjm[3 * kHjLd + min_idx];
+                        h.zr = hjm[4 * kHjLd + min_idx];
+                        h.zphi = hjm[5 * kHjLd + min_idx];
+                    }
                     gather_rows(G3, G4, C, rob, lane, min_idx);
+                    TILE_PROF_MARK(12);
                     gain_w<false>(G3, G4, Wab, nullptr, rob, wa, wa, lane, min_idx, h);
+                    TILE_PROF_MARK(13);
                     gain_k(Wab, Kab, st, rob, stl, wa, lane, min_idx, h, __dsub_rn(zr, h.zr),
                            normalize_angle(__dsub_rn(zphi, h.zphi)));  // :182-183
+                    TILE_PROF_MARK(14);
                     pass_blocks<false>(C, Kab, Wab, lane);  // the next distances need the new Sigma
                     __syncwarp();
                     if (!staged_next) stage_next();
                     mirrors_stale = true;
                     ++n_corr;
                     assoc = min_idx;
+                    TILE_PROF_MARK(15);
                 }
                 if (lane == 0) {
                     if (p.assoc_out) p.assoc_out[o] = assoc;

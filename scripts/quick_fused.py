@@ -78,6 +78,8 @@ def main():
             tot = float(sum(buf))
             names = ["inputs", "wait landing", "regs+predict", "meas entry", "corr (rest)", "write-back", "-", "loop top",
                      "gain_w A", "gain_k A", "robcols+H_j B", "gain_w B", "gain_k B", "last pass", "H_j A' || pass", "stage+gather"]
+            if a.unknown:
+                names[8:] = ["mirrors", "distances", "argmin+gates", "creation", "H_j+gather", "gain_w", "gain_k", "pass+stage"]
             print("   phase cycles per filter-step: " + ", ".join(
                 f"{n_} {buf[k] / (a.steps * B):.0f} ({100 * buf[k] / tot:.0f}%)" for k, n_ in enumerate(names) if buf[k]))
         print(f"rep {rep}: {ms / a.steps:.4f} ms/step, {upd / a.steps / B:.2f} upd/filter-step, "
