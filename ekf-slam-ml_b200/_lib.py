@@ -132,7 +132,7 @@ SIGNATURES = {
 }
 
 # include/ekf_sharded_b200.h (separate library: it links NCCL)
-SHARDED_LIB_PATH = os.path.join(_HERE, "libekfslam_sharded_b200.so")
+SHARDED_LIB_PATH = os.environ.get("EKF_B200_SHARDED_LIB") or os.path.join(_HERE, "libekfslam_sharded_b200.so")
 SIGNATURES_SHARDED = {
     "ekf_sharded_last_error": (ctypes.c_char_p, []),
     "ekf_sharded_unique_id": (ctypes.c_int, [ctypes.c_void_p]),

@@ -10,6 +10,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -223,7 +224,12 @@ __global__ void __launch_bounds__(256)
 // Slot p = the pending-factor slot of the correction, source 0 = rank 0's partial, source 1 = the landmark owner's.  A flag
 // holds the group generation number of the data it guards; slots are reused only after the group's sweep, which is
 // preceded by a barrier across the ranks.
-constexpr size_t kXFlagBytes = 256;
+// (The two-kernel variant keeps one flag per (slot, source); the fused kernel one per (slot, source, 256-column
+// block), so the flag region is sized for the latter.)
+__host__ __device__ inline size_t xflag_blocks(long long ld) { return (size_t)((ld + 255) / 256); }
+__host__ __device__ inline size_t xflag_bytes(long long ld) {
+    return ((size_t)kMaxPending * 2 * xflag_blocks(ld) * sizeof(unsigned long long) + 255) & ~(size_t)255;
+}
 __host__ __device__ inline size_t xdata_index(int p, int src, long long ld) { return ((size_t)p * 2 + src) * (size_t)ld; }
 
 __device__ __forceinline__ void st_sys_v2(double2* ptr, double2 v) {  // also valid on a multicast address
@@ -321,8 +327,8 @@ __global__ void __launch_bounds__(256)
         }
         // rank 0 owning the landmark: its partial is the whole W (source 0) and source 1 is zero
         const double2 zero = make_double2(0.0, 0.0);
-        const size_t o0 = kXFlagBytes + (xdata_index(p, 0, ld) + (size_t)c) * sizeof(double2);
-        const size_t o1 = kXFlagBytes + (xdata_index(p, 1, ld) + (size_t)c) * sizeof(double2);
+        const size_t o0 = xflag_bytes(ld) + (xdata_index(p, 0, ld) + (size_t)c) * sizeof(double2);
+        const size_t o1 = xflag_bytes(ld) + (xdata_index(p, 1, ld) + (size_t)c) * sizeof(double2);
         if (xp.mc) {
             if (push0) mc_st_v2(reinterpret_cast<double2*>(xp.mc + o0), w);
             if (push1) mc_st_v2(reinterpret_cast<double2*>(xp.mc + o1), rank == 0 ? zero : w);
@@ -361,8 +367,8 @@ __global__ void __launch_bounds__(256)
     __shared__ double nu_s[2];
     __shared__ int active_s;
     pdl_prologue();
-    const double2* x0 = reinterpret_cast<const double2*>(xlocal + kXFlagBytes) + xdata_index(p, 0, ld);
-    const double2* x1 = reinterpret_cast<const double2*>(xlocal + kXFlagBytes) + xdata_index(p, 1, ld);
+    const double2* x0 = reinterpret_cast<const double2*>(xlocal + xflag_bytes(ld)) + xdata_index(p, 0, ld);
+    const double2* x1 = reinterpret_cast<const double2*>(xlocal + xflag_bytes(ld)) + xdata_index(p, 1, ld);
     if (threadIdx.x == 0) {
         const unsigned long long* fl = reinterpret_cast<const unsigned long long*>(xlocal) + (size_t)p * 2;
         while (ld_acquire_sys_u64(fl) != gen) {
@@ -406,6 +412,205 @@ __global__ void __launch_bounds__(256)
     double ns = state[k] + fma(k1, nu_s[1], k0 * nu_s[0]);
     if (k == 0) ns = normalize_angle(ns);  // ekf_slam.cpp:187
     state[k] = ns;
+}
+
+
+#ifndef EKF_SH_PROF
+#define EKF_SH_PROF 0  // 1: per-phase globaltimer stamps of the fused correction kernel (development builds only)
+#endif
+#if EKF_SH_PROF
+__device__ unsigned long long g_sh_prof[2][8];
+__device__ __forceinline__ unsigned long long gtime() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+#define SH_MARK(k)                                                                  \
+    do {                                                                            \
+        if (threadIdx.x == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1))   \
+            g_sh_prof[blockIdx.x == 0 ? 0 : 1][k] = gtime();                        \
+    } while (0)
+#else
+#define SH_MARK(k) \
+    do {           \
+    } while (0)
+#endif
+
+// The whole correction in ONE launch (the default push path).  Per 256-column block b of a rank:
+//   source ranks (rank 0: rows 0..2; the landmark's owner: rows 3+2i, 4+2i): rebuild the owned rows' column entries
+//   with the pending factors, form the partial W, store it into every rank's slot and raise the block's flag;
+//   every rank: wait for the flags of block b and of the blocks holding columns {0,1,2,3+2i,4+2i} (they carry S),
+//   then W = sum of the partials, S^-1, K, the state update and the factor slot for the sweep.
+// A CTA pushes before it waits and waits only on pushes, and with programmatic stream serialisation a successor's CTAs
+// are admitted only after every CTA of this grid has started, so all flags a CTA waits for are eventually raised.
+// Flags of this variant: [kMaxPending][2 sources][256-column blocks] uint64 (same data layout as above).
+// Measured (2 GPUs, N = 80,003): ~2.5 us pose/landmark/H_j and row loads, ~2 us partial W + stores, ~10 us until the
+// 1.3 MB of partials are visible on the peers (the release fence waits for the multicast acknowledgements; sending
+// self-validating lines instead of data + flag moved twice the bytes in the same time), ~1 us S^-1.
+__global__ void __launch_bounds__(256)
+    k_sh_correct_push(const double* __restrict__ sig_local, long long ld, long long r0, long long r1, long long r1_rank0, int N,
+                      int rank, double* __restrict__ state, const double* __restrict__ pose_src,
+                      const UpdateCmd* __restrict__ cmd, int lm_arg, double sx_arg, double sy_arg, double2* __restrict__ Kall,
+                      double2* __restrict__ Wall, int p, const XPeers xp, const unsigned char* __restrict__ xlocal,
+                      unsigned long long gen, unsigned long long* __restrict__ read_count, unsigned long long read_target) {
+    __shared__ Hj h_s;
+    __shared__ double z_s[2], nu_s[2];
+    __shared__ Sym2 si_s;
+    __shared__ double2 kidx_s[kMaxPending][5];
+    SH_MARK(0);
+    pdl_prologue();
+    SH_MARK(1);
+    int lm = lm_arg, active = 1;
+    double sx = sx_arg, sy = sy_arg;
+    if (cmd) {
+        active = cmd->do_update;
+        lm = cmd->lm;
+        sx = cmd->sx;
+        sy = cmd->sy;
+    }
+    const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    double2* Wslot = Wall + (long long)p * ld;
+    double2* Kout = Kall + (long long)p * ld;
+    if (!active) {  // a dropped measurement: every rank knows (the command block is replicated), nothing is exchanged
+        if (threadIdx.x == 0) atomicAdd(read_count, 1ull);
+        if (c < ld) {
+            Wslot[c] = make_double2(0.0, 0.0);
+            Kout[c] = make_double2(0.0, 0.0);
+        }
+        return;
+    }
+    const long long i3 = 3 + 2 * (long long)lm;
+    const bool two_sources = i3 >= r1_rank0;  // the landmark's rows are not rank 0's
+    const bool owns_lm = i3 >= r0 && i3 < r1;
+    const bool source = rank == 0 || owns_lm;
+    const int my_src = rank == 0 ? 0 : 1;
+    const long long id[5] = {0, 1, 2, i3, i3 + 1};
+    const size_t nblk = xflag_blocks(ld);
+    // Thread 0 of every CTA reads the pose and the landmark from the state that other CTAs update at the end of this
+    // same kernel: it counts itself in once it has them, and the (at most three) CTAs that own those elements hold
+    // their state update back until every CTA of the grid has counted in.
+    if (threadIdx.x == 0) {
+        const double lx = state[i3], ly = state[i3 + 1], p0 = pose_src[0], p1 = pose_src[1], p2 = pose_src[2];
+        h_s = make_hj(lx, ly, p0, p1, p2);
+        __threadfence();
+        atomicAdd(read_count, 1ull);
+        double zr, zphi;
+        range_bearing(sx, sy, zr, zphi);
+        z_s[0] = zr;
+        z_s[1] = zphi;
+    }
+    double sv[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+    bool own[5] = {false, false, false, false, false};
+    if (source) {
+        if (threadIdx.x >= 32 && threadIdx.x < 37) {
+            const int k = threadIdx.x - 32;
+            if (id[k] >= r0 && id[k] < r1)
+                for (int j = 0; j < p; ++j) kidx_s[j][k] = Kall[(long long)j * ld + id[k]];
+        }
+        if (c < N) {
+#pragma unroll
+            for (int k = 0; k < 5; ++k) {
+                own[k] = id[k] >= r0 && id[k] < r1;
+                sv[k] = own[k] ? sig_local[(id[k] - r0) * ld + c] : 0.0;
+            }
+        }
+    }
+    __syncthreads();
+    SH_MARK(2);
+    if (source) {
+        if (c < ld) {
+            double2 w = make_double2(0.0, 0.0);
+            if (c < N) {
+#pragma unroll 4
+                for (int j = 0; j < p; ++j) {
+                    const double2 wj = Wall[(long long)j * ld + c];
+#pragma unroll
+                    for (int k = 0; k < 5; ++k)
+                        if (own[k]) sv[k] = apply_factor(sv[k], kidx_s[j][k], wj);
+                }
+                const Hj h = h_s;
+                w = make_double2(h_row0(h, sv[1], sv[2], sv[3], sv[4]), h_row1(h, sv[0], sv[1], sv[2], sv[3], sv[4]));
+            }
+            const size_t o = xflag_bytes(ld) + (xdata_index(p, my_src, ld) + (size_t)c) * sizeof(double2);
+            if (xp.mc) {
+                mc_st_v2(reinterpret_cast<double2*>(xp.mc + o), w);
+            } else {
+                for (int g = 0; g < xp.world; ++g) st_sys_v2(reinterpret_cast<double2*>(xp.base[g] + o), w);
+            }
+        }
+        SH_MARK(3);
+        // the CTA's stores happen before the barrier; thread 0's system-scope fence after it (inside the release
+        // below) is cumulative over them, so one fence per CTA orders the whole block's partial before its flag
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const size_t of = (((size_t)p * 2 + my_src) * nblk + blockIdx.x) * sizeof(unsigned long long);
+            if (xp.mc) {
+                mc_st_release_u64(reinterpret_cast<unsigned long long*>(xp.mc + of), gen);
+            } else {
+                for (int g = 0; g < xp.world; ++g)
+                    st_release_sys_u64(reinterpret_cast<unsigned long long*>(xp.base[g] + of), gen);
+            }
+        }
+        SH_MARK(4);
+    }
+    // ---- every rank: the partials of this block and of the blocks that carry S
+    if (threadIdx.x < 8) {
+        const int src = threadIdx.x & 1, which = threadIdx.x >> 1;
+        if (src == 0 || two_sources) {
+            const size_t blk = which == 0 ? (size_t)blockIdx.x : which == 1 ? 0 : (size_t)((i3 + (which - 2)) >> 8);
+            const unsigned long long* fl = reinterpret_cast<const unsigned long long*>(xlocal) + ((size_t)p * 2 + src) * nblk + blk;
+            while (ld_acquire_sys_u64(fl) != gen) {
+            }
+        }
+    }
+    __syncthreads();
+    SH_MARK(6);
+    const double2* x0 = reinterpret_cast<const double2*>(xlocal + xflag_bytes(ld)) + xdata_index(p, 0, ld);
+    const double2* x1 = reinterpret_cast<const double2*>(xlocal + xflag_bytes(ld)) + xdata_index(p, 1, ld);
+    if (threadIdx.x == 0) {
+        const Hj h = h_s;
+        double2 w5[5];
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+            w5[k] = __ldcg(x0 + id[k]);
+            if (two_sources) {
+                const double2 b = __ldcg(x1 + id[k]);
+                w5[k] = make_double2(w5[k].x + b.x, w5[k].y + b.y);
+            }
+        }
+        const double s00 = h_row0(h, w5[1].x, w5[2].x, w5[3].x, w5[4].x) + kR;
+        const double s01 = h_row1(h, w5[0].x, w5[1].x, w5[2].x, w5[3].x, w5[4].x);
+        const double s10 = h_row0(h, w5[1].y, w5[2].y, w5[3].y, w5[4].y);
+        const double s11 = h_row1(h, w5[0].y, w5[1].y, w5[2].y, w5[3].y, w5[4].y) + kR;
+        si_s = inv2x2(s00, s01, s10, s11);
+        nu_s[0] = __dsub_rn(z_s[0], h.zr);
+        nu_s[1] = normalize_angle(__dsub_rn(z_s[1], h.zphi));
+        const long long b0 = (long long)blockIdx.x << 8, b1 = b0 + 256;
+        if (b0 < 3 || (i3 + 1 >= b0 && i3 < b1)) {  // this CTA's state update overwrites what thread 0 of the others reads
+            while (ld_acquire_sys_u64(read_count) < read_target) {
+            }
+        }
+    }
+    __syncthreads();
+    SH_MARK(7);
+    if (c >= ld) return;
+    if (c >= N) {
+        Wslot[c] = make_double2(0.0, 0.0);
+        Kout[c] = make_double2(0.0, 0.0);
+        return;
+    }
+    double2 w = __ldcg(x0 + c);
+    if (two_sources) {
+        const double2 b = __ldcg(x1 + c);
+        w = make_double2(w.x + b.x, w.y + b.y);
+    }
+    Wslot[c] = w;
+    const Sym2 si = si_s;
+    const double k0 = fma(w.y, si.i10, w.x * si.i00), k1 = fma(w.y, si.i11, w.x * si.i01);
+    Kout[c] = make_double2(k0, k1);
+    double ns = state[c] + fma(k1, nu_s[1], k0 * nu_s[0]);
+    if (c == 0) ns = normalize_angle(ns);  // ekf_slam.cpp:187
+    state[c] = ns;
 }
 
 // ---- association
@@ -570,6 +775,9 @@ struct ekf_sharded {
     unsigned long long gen = 1;     // group generation: what a raised flag holds
     unsigned int* d_done2 = nullptr;
     int* d_barrier = nullptr;
+    bool push_fused = true;               // one kernel per correction (EKF_SHARDED_PUSH_TWO_KERNELS=1: the two-kernel variant)
+    unsigned long long* d_read_count = nullptr;
+    unsigned long long corrections_enqueued = 0;
     int rank = 0;
 };
 
@@ -759,6 +967,19 @@ int settle(ekf_sharded* h) { return h->pending ? flush(h, h->pending, false) : 0
 int correct(ekf_sharded* h, bool use_cmd, bool stale_pose, int lm, double sx, double sy) {
     const int gl = (int)((h->ld + 255) / 256);
     const int p = h->pending;
+    if (h->push && h->push_fused) {
+        Shard& s = h->sh[0];
+        h->corrections_enqueued += 1;
+        CU(launch_pdl(k_sh_correct_push, dim3(gl), dim3(256), 0, h->stream, (const double*)s.sig, h->ld, s.r0, s.r1, h->r1_of[0], h->N,
+                      h->rank, s.state, (const double*)(stale_pose ? s.pose0 : s.state),
+                      (const UpdateCmd*)(use_cmd ? s.cmd : nullptr), lm, sx, sy, s.K2, s.W2, p, h->xp,
+                      (const unsigned char*)h->xlocal, h->gen, h->d_read_count,
+                      h->corrections_enqueued * (unsigned long long)gl));
+        h->launches += 1;
+        h->pending += 1;
+        if (!use_cmd && h->pending == kMaxPending) return flush(h, kMaxPending, false);
+        return 0;
+    }
     if (h->push) {
         Shard& s = h->sh[0];
         CU(launch_pdl(k_sh_wpart_push, dim3(gl), dim3(256), 0, h->stream, (const double*)s.sig, h->ld, s.r0, s.r1, h->N, h->rank,
@@ -882,6 +1103,7 @@ int ekf_sharded_destroy(ekf_sharded* h) {
     }
     if (h->d_srcs) cudaFree((void*)h->d_srcs);
     cudaFree(h->d_done2);
+    cudaFree(h->d_read_count);
     cudaFree(h->d_barrier);
     if (h->h_stage) cudaFreeHost(h->h_stage);
     if (h->comm) ncclCommDestroy(h->comm);
@@ -929,9 +1151,14 @@ int ekf_sharded_create(int n, int rank, int world, const void* id128, int device
 // into this process for every rank (peer_bases[rank'], rank' = 0..world-1), plus the multicast address of the same
 // buffer when the fabric has one (0 otherwise).  Collective: every rank attaches before the next verb.  The buffers
 // stay the caller's; they must outlive the handle.  Without this call the exchange is an ncclAllReduce.
+#if EKF_SH_PROF
+int ekf_sharded_debug_prof(uint64_t* out16) {
+    return cudaMemcpyFromSymbol(out16, g_sh_prof, sizeof(uint64_t) * 16) == cudaSuccess ? 0 : -1;
+}
+#endif
 int ekf_sharded_exchange_bytes(ekf_sharded* h, uint64_t* bytes) {
     if (!h || !bytes) return fail(-1, "null argument");
-    *bytes = kXFlagBytes + (uint64_t)kMaxPending * 2 * (uint64_t)h->ld * sizeof(double2);
+    *bytes = xflag_bytes(h->ld) + (uint64_t)kMaxPending * 2 * (uint64_t)h->ld * sizeof(double2);
     return 0;
 }
 int ekf_sharded_attach_exchange(ekf_sharded* h, int world, const uint64_t* peer_bases, uint64_t multicast_base) {
@@ -954,6 +1181,17 @@ int ekf_sharded_attach_exchange(ekf_sharded* h, int world, const uint64_t* peer_
         CU(cudaMalloc(&h->d_barrier, sizeof(int)));
         CU(cudaMemset(h->d_done2, 0, sizeof(unsigned int)));
         CU(cudaMemset(h->d_barrier, 0, sizeof(int)));
+        CU(cudaMalloc(&h->d_read_count, sizeof(unsigned long long)));
+        CU(cudaMemset(h->d_read_count, 0, sizeof(unsigned long long)));
+        h->corrections_enqueued = 0;
+    }
+    {
+        const char* two = getenv("EKF_SHARDED_PUSH_TWO_KERNELS");
+        h->push_fused = !(two && two[0] == '1');
+        // the fused kernel's CTAs wait for one another: the whole grid has to be resident at once
+        int per_sm = 0;
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sh_correct_push, 256, 0));
+        if ((h->ld + 255) / 256 > (long long)per_sm * h->sm_count) h->push_fused = false;
     }
     h->gen = 1;
     h->push = true;
