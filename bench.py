@@ -331,8 +331,8 @@ def large_map_leg(pkg, device, n_lm, timed_updates, peak_gbs, want_cpu):
         "roofline": {"bound": "hbm", "kernel": "k_large_sweep_mma<P> (time per sweep = whole step incl. predict + gains)",
                      "achieved": alg_bytes * n_sweeps / (sweep_ms_total * 1e-3) / 1e9, "peak": peak_gbs, "unit": "GB/s",
                      "frac": alg_bytes * n_sweeps / (sweep_ms_total * 1e-3) / 1e9 / peak_gbs,
-                     # ncu capture profiles/r1_prof_sweep_tma_raw.csv (P = 12): 2.220 GB read + 2.096 GB written per launch
-                     "traffic": 4.316e9 if n_lm == 8192 else None,
+                     # ncu capture profiles/r2_prof_sweep_mma_raw.csv (P = 14): 2.235 GB read + 2.091 GB written per launch
+                     "traffic": 4.326e9 if n_lm == 8192 else None,
                      "algorithmic_bytes_per_launch": alg_bytes, "sweeps": n_sweeps,
                      "updates_per_sweep": done / max(n_sweeps, 1),
                      "per_update_achieved": alg_bytes / (ms_upd * 1e-3) / 1e9,
@@ -864,7 +864,7 @@ def run_ours(args):
         "achieved": step_bytes / (kern_ms_avg * 1e-3) / 1e9,
         "frac": step_bytes / (kern_ms_avg * 1e-3) / 1e9 / peak_gbs,
         # dram__bytes_read.sum + dram__bytes_write.sum per launch of this kernel at this batch size, from the committed
-        # ncu --set full capture (profiles/r2_prof_fused_tile_raw.csv); not re-measured here
+        # ncu --set full capture (profiles/r2_prof_fused_tile_raw.csv: 619.4 MB read + 536.9 MB written); not re-measured here
         "traffic": 1.156e9 if (B == FILTERS_PER_GPU and tiled) else None,
         "algorithmic_bytes_per_launch": step_bytes,
         "stored_bytes_per_launch": stored_bytes,
