@@ -288,6 +288,36 @@ def parity_sharded(pkg, dist, local, n_lm, tr, min_corrections=10, sample_rows=N
 
 
 # ----------------------------------------------------------------------------- our arm
+def cpu_reference_dense_scaling(pkg):
+    """the reference's own dense filter (oracle/_ref, one core) at growing map sizes, to show the
+    cubic law that makes it intractable at cfg4 (2 N^3 flop per correction).  Whole-step time per correction."""
+    import _oracle
+    L = _oracle.ref_lib()
+    if L is None:
+        return None
+    tg = pkg.tracegen
+    rows = []
+    for (nx, ny, steps) in ((5, 4, 120), (10, 10, 24), (25, 20, 4)):
+        n = nx * ny
+        tr = tg.simulate_known(tg.grid_world(nx, ny, pitch=0.5, n_slots=n, max_visible=0.7), 1, steps, seed=5)
+        tw = np.ascontiguousarray(tr["twists"].transpose(1, 0, 2))
+        xy = np.ascontiguousarray(tr["xy"].transpose(1, 0, 2))
+        vis = np.ascontiguousarray(tr["vis"].transpose(1, 0, 2))
+        upd = ctypes.c_int64()
+        sec = L.ref_bench_known(n, 1, steps, tw.ctypes.data_as(ctypes.POINTER(ctypes.c_double)),
+                                xy.ctypes.data_as(ctypes.POINTER(ctypes.c_double)),
+                                vis.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)), ctypes.byref(upd), None)
+        rows.append({"n_landmarks": n, "state_dim": 3 + 2 * n, "corrections": int(upd.value), "steps": steps,
+                     "ms_per_correction": 1e3 * sec / max(1, upd.value)})
+    a, b = rows[-2], rows[-1]
+    expo = float(np.log(b["ms_per_correction"] / a["ms_per_correction"]) / np.log(b["state_dim"] / a["state_dim"]))
+    return {"kind": "reference", "cores": 1, "sizes": rows, "exponent_between_last_two": expo,
+            "extrapolated_s_per_correction_at_N16387": 1e-3 * b["ms_per_correction"] * (16387.0 / b["state_dim"]) ** 3,
+            "note": "reference ekf_slam.cpp, dense (I - K H) Sigma and A Sigma A^T GEMMs over single-thread OpenBLAS; the step's "
+                    "prediction is included in the per-correction time"}
+
+
+
 def large_map_leg(pkg, device, n_lm, timed_updates, peak_gbs, want_cpu):
     """cfg4: one filter, n_lm landmarks; streamed gain + sweep per correction."""
     tg = pkg.tracegen
@@ -346,6 +376,9 @@ def large_map_leg(pkg, device, n_lm, timed_updates, peak_gbs, want_cpu):
     out["parity"] = par
     if want_cpu:
         out["cpu_baseline"] = cpu
+        dense = cpu_reference_dense_scaling(pkg)
+        if dense is not None:
+            out["cpu_baseline"]["dense_reference_scaling"] = dense
     return out
 
 
