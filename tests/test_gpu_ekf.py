@@ -502,7 +502,12 @@ def test_golden_known_association(gpu_pkg, engine):
 
 @pytest.mark.parametrize("engine", ["fused", "stream"])
 def test_golden_unknown_association(gpu_pkg, engine):
-    """tests/golden/ekf_unknown_n20.npz: the reference's known_list after every call, state / Sigma checkpoints."""
+    """tests/golden/ekf_unknown_n20.npz: the reference's known_list after every call, state / Sigma checkpoints.
+
+    What comes from where: `known`, `state`, `sigma` were produced by the REFERENCE build (oracle/_ref).  The reference
+    exposes no per-measurement association index (it only prints), so `assoc_from_restatement` was produced by
+    oracle/ekf_oracle.c on the same run; the reference-owned checkpoints of state and Sigma are what close the loop on
+    those indices (a different association would move them far beyond the tolerance)."""
     g = np.load(_os.path.join(_GOLD, "ekf_unknown_n20.npz"))
     f = gpu_pkg.EKF_SLAM(20, engine=gpu_pkg.ENGINE_FUSED if engine == "fused" else gpu_pkg.ENGINE_STREAM)
     known = np.zeros(20, np.uint8)
