@@ -144,6 +144,43 @@ def test_maha_seam_and_getters(gpu_pkg):
     assert np.array_equal(g.state, f.state) and np.array_equal(g.sigma, f.sigma)
 
 
+def test_pose_read_path_follows_every_way_the_state_can_change(gpu_pkg):
+    """The small engine leaves the pose in mapped pinned memory and the facades serve theta / x / y from one read; every
+    verb that changes the state - including the ones that do not launch the fused kernel - must be seen by the getters."""
+    import ctypes
+    tr = _trace(gpu_pkg, 20, 6, seed=8)
+    f = gpu_pkg.EKF_SLAM(20)
+    o = OracleEKF(20)
+    for t in range(3):
+        f.prediction(tuple(tr["twists"][t, 0]))
+        o.prediction(*tr["twists"][t, 0])
+        assert abs(f.getStateTheta() - o.state[0]) < 1e-12 and abs(f.getStateX() - o.state[1]) < 1e-12
+        f.measurement(tr["xy"][t, 0], tr["vis"][t, 0])
+        o.measurement(tr["xy"][t, 0], tr["vis"][t, 0])
+        assert abs(f.getStateTheta() - o.state[0]) < 1e-11 and abs(f.getStateY() - o.state[2]) < 1e-11
+        assert np.allclose(f.state[:3], [f.getStateTheta(), f.getStateX(), f.getStateY()], rtol=0, atol=0)
+    s = f.state
+    s[:3] = [0.25, -1.5, 2.75]
+    f.state = s                                    # set_state: a plain copy, no kernel
+    assert (f.getStateTheta(), f.getStateX(), f.getStateY()) == (0.25, -1.5, 2.75)
+    f.prediction((0.0, 0.0))                       # back on the kernel path
+    assert f.getStateX() == f.state[1] and f.getStateTheta() == f.state[0]
+    g = f.clone()
+    assert g.getStateX() == f.getStateX() and g.getStateY() == f.getStateY()
+    # a caller that took the device pointers may write the state behind the handle: the getter must read the device
+    L = gpu_pkg._lib.load()
+    st = ctypes.c_void_p()
+    assert L.ekf_device_pointers(f._h, None, None, ctypes.byref(st)) == 0 and st.value
+    import torch
+
+    class _View:  # three doubles at the state pointer, as a CUDA array
+        __cuda_array_interface__ = {"shape": (3,), "typestr": "<f8", "data": (st.value, False), "version": 2}
+    torch.as_tensor(_View(), device="cuda").copy_(torch.tensor([1.0, 2.0, 3.0], dtype=torch.float64))
+    torch.cuda.synchronize()
+    f._pose_cache = None  # the Python facade caches per verb; the write above went around it
+    assert (f.getStateTheta(), f.getStateX(), f.getStateY()) == (1.0, 2.0, 3.0)
+
+
 def test_normalize_angle_device_twin_is_bit_exact(gpu_pkg):
     """rigid2d::normalize_angle: the device twin must equal the C library fmod formulation bit for bit."""
     import ctypes
