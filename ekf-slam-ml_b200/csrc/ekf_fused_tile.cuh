@@ -320,6 +320,23 @@ __device__ __forceinline__ Innov make_innov_nobranch(double mx, double my, doubl
     h.nu1 = fma(sn * x2, pl, sn);
     return h;
 }
+// Range and unit direction of a reading without the library's sqrt and division (each with a slow-path branch): the
+// rsqrt of the normal range, one correction step for the range, products for the direction; zero / subnormal /
+// infinite / NaN arguments take make_reading() out of line.
+static __device__ __noinline__ Reading make_reading_cold(double sx, double sy) { return make_reading(sx, sy); }
+__device__ __forceinline__ Reading make_reading_fast(double sx, double sy) {
+    const double d = __dadd_rn(__dmul_rn(sx, sx), __dmul_rn(sy, sy));
+    bool special;
+    const double isq = rsqrt_normal_range(d, special);
+    Reading z;
+    const double r0 = __dmul_rn(d, isq);
+    z.zr = fma(fma(-r0, r0, d), 0.5 * isq, r0);
+    z.ux = __dmul_rn(sx, isq);
+    z.uy = __dmul_rn(sy, isq);
+    if (special) z = make_reading_cold(sx, sy);
+    return z;
+}
+
 static __device__ __noinline__ Innov make_innov_cold(double mx, double my, double theta, double sth, double cth, double x,
                                                      double y, double zr, double ux, double uy) {
     return make_innov(mx, my, theta, sth, cth, x, y, Reading{zr, ux, uy});
@@ -467,7 +484,7 @@ __global__ void __launch_bounds__(32, EKF_TILE_MINB) ekf_fused_tile_kernel(const
                     const double sx = ldg_f64_early(p.xy + 2 * (long long)(sp_begin + k)),
                                  sy = ldg_f64_early(p.xy + 2 * (long long)(sp_begin + k) + 1);
                     id = (int)ldg_u8_early(p.vis + sp_begin + k);
-                    const Reading z = make_reading(sx, sy);
+                    const Reading z = make_reading_fast(sx, sy);
                     if (id < n) {
                         zbuf[3 * id] = z.zr;
                         zbuf[3 * id + 1] = z.ux;
@@ -482,7 +499,7 @@ __global__ void __launch_bounds__(32, EKF_TILE_MINB) ekf_fused_tile_kernel(const
             const unsigned vb = ldg_u8_early(p.vis + b * n + ls);
             vismask = __ballot_sync(kFull, lane < n && vb != 0);
             if (lane < n) {  // range and unit direction of every slot's reading (ekf_slam.cpp:140-146)
-                const Reading z = make_reading(sx, sy);
+                const Reading z = make_reading_fast(sx, sy);
                 zbuf[3 * lane] = z.zr;
                 zbuf[3 * lane + 1] = z.ux;
                 zbuf[3 * lane + 2] = z.uy;
@@ -624,8 +641,12 @@ __global__ void __launch_bounds__(32, EKF_TILE_MINB) ekf_fused_tile_kernel(const
                 int ia = __ffs(rem) - 1;
                 rem &= rem - 1;
                 int ib = rem ? __ffs(rem) - 1 : -1;  // the pair's second landmark, if any
-                Innov h = make_innov(st[3 + 2 * ia], st[4 + 2 * ia], theta, sth, cth, x, y,
-                                     Reading{zbuf[3 * ia], zbuf[3 * ia + 1], zbuf[3 * ia + 2]});
+                bool slow0 = false;
+                Innov h = make_innov_nobranch(st[3 + 2 * ia], st[4 + 2 * ia], sth, cth, x, y,
+                                              Reading{zbuf[3 * ia], zbuf[3 * ia + 1], zbuf[3 * ia + 2]}, slow0);
+                if (slow0)
+                    h = make_innov_cold(st[3 + 2 * ia], st[4 + 2 * ia], theta, sth, cth, x, y, zbuf[3 * ia], zbuf[3 * ia + 1],
+                                        zbuf[3 * ia + 2]);
                 // both landmarks' rows come from the same landmark blocks (no pass in between); only the robot
                 // columns of the second one's rows wait for the first correction
                 gather_rows(G3, G4, C, rob, lane, ia);
