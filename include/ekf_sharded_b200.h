@@ -6,7 +6,9 @@
  * Partition: rank g owns the rows of landmarks [L_g, L_g+1) (two rows each, never split) and rank 0 additionally
  * the three robot rows; every rank holds all N columns of its rows, a replica of the state vector, and runs the
  * rank-2 sweep on its own rows only.  Per correction the ranks exchange
- *   W = Hj*Sigma (2 x N): all-reduce of the owners' partial products (W comes from ROWS, as in the reference);
+ *   W = Hj*Sigma (2 x N): the sum of the owners' partial products (W comes from ROWS, as in the reference) - an
+ *   ncclAllReduce, or, with an attached exchange buffer (below), stores of the at most two non-zero partials into every
+ *   rank's buffer from inside the correction kernel;
  *   every replica then forms K = W^T S^-1 (Sigma symmetric) and the state update locally, so K is not exchanged;
  * per associated measurement additionally the 3 x N robot rows (broadcast from rank 0) and one 24-byte
  * (distance, runner-up, index) triple per rank.
@@ -33,8 +35,8 @@ int ekf_sharded_create_local(int n_landmarks, int world, int device, ekf_sharded
 int ekf_sharded_destroy(ekf_sharded* h);
 /* Optional: exchange W without a collective.  Per correction only rank 0 (robot rows) and the landmark's owner hold
  * non-zero parts of W = Hj*Sigma; with an attached exchange buffer they store their parts straight into every rank's
- * buffer over NVLink (through the NVSwitch multicast address when one is given) and the gain kernel waits on flags
- * instead of on an ncclAllReduce.  The caller allocates one symmetric, zero-filled buffer of
+ * buffer over NVLink (through the NVSwitch multicast address when one is given) and the correction kernel - one launch
+ * for partial W, stores, flags, gain and state update - waits on per-block flags instead of on an ncclAllReduce.  The caller allocates one symmetric, zero-filled buffer of
  * ekf_sharded_exchange_bytes() bytes per rank (e.g. torch.distributed._symmetric_memory, or cudaIpc) and passes every
  * rank's mapping of it (peer_bases[0..world-1]) and the multicast address (0 = none).  Collective; the buffers must
  * outlive the handle.  Results are identical to the all-reduce path. */
