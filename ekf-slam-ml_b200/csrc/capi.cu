@@ -283,6 +283,11 @@ struct ekf_filter {
     // Fused engine: the kernels read their inputs from the pinned ring and leave the pose in h_pose through the
     // device mapping of that memory (no copy commands on the stream; a step is launch + synchronise).
     double* h_pose = nullptr;
+    // prediction() on the small engine is deferred: the twist waits here and rides along with the next measurement() /
+    // data_association() kernel (mode kDoPredict | ...), one launch and one round trip of Sigma instead of two; any other
+    // verb that looks at or changes the filter applies it first (stream_settle).
+    bool pred_pending = false;
+    double pred_tw[2] = {0.0, 0.0};
     bool pose_host_ok = false;  // h_pose holds the pose of the last enqueued kernel
     bool external = false;      // ekf_device_pointers() handed the state out: h_pose can no longer be trusted
     size_t h_out_bytes = 0;
@@ -453,8 +458,31 @@ int stream_correct(ekf_filter* h, const double* pose_src, const UpdateCmd* cmd, 
 
 // Verbs that look at Sigma or at the update counter first bring Sigma up to date (factors may stay pending across
 // prediction() and measurement() calls).
+int fused_flush_predict(ekf_filter* h) {
+    if (!h->pred_pending) return EKF_OK;
+    unsigned char* slot;
+    cudaEvent_t ev;
+    int rc = ring_acquire(h, &slot, &ev);
+    if (rc) return rc;
+    double* tw = reinterpret_cast<double*>(slot);
+    tw[0] = h->pred_tw[0];
+    tw[1] = h->pred_tw[1];
+    FusedParams p = fused_params(h, kDoPredict, 1);
+    p.twists = tw;  // read through the device mapping of the pinned slot
+    rc = launch_fused(p, h->stream, h->device);
+    CU(cudaEventRecord(ev, h->stream));
+    h->launches += 1;
+    h->pose_host_ok = rc == EKF_OK;
+    h->pred_pending = false;
+    return rc;
+}
+
+// verbs that only look at the state vector: the streamed engine's pending Sigma factors may stay pending
+int settle_prediction(ekf_filter* h) { return h->engine == EKF_ENGINE_FUSED ? fused_flush_predict(h) : EKF_OK; }
+
 int stream_settle(ekf_filter* h) {
-    if (h->engine == EKF_ENGINE_FUSED || h->pending == 0) return EKF_OK;
+    if (h->engine == EKF_ENGINE_FUSED) return fused_flush_predict(h);
+    if (h->pending == 0) return EKF_OK;
     return stream_flush(h, h->pending, nullptr);
 }
 
@@ -619,20 +647,12 @@ int ekf_predict(ekf_filter* h, double dtheta, double dx) {
     if (!h) return fail(EKF_ERR_INVALID, "null handle");
     DeviceGuard g(h->device);
     if (h->engine == EKF_ENGINE_FUSED) {
-        unsigned char* slot;
-        cudaEvent_t ev;
-        int rc = ring_acquire(h, &slot, &ev);
+        int rc = fused_flush_predict(h);  // two predictions in a row: the earlier one goes first, on its own
         if (rc) return rc;
-        double* tw = reinterpret_cast<double*>(slot);
-        tw[0] = dtheta;
-        tw[1] = dx;
-        FusedParams p = fused_params(h, kDoPredict, 1);
-        p.twists = tw;  // read through the device mapping of the pinned slot
-        rc = launch_fused(p, h->stream, h->device);
-        CU(cudaEventRecord(ev, h->stream));
-        h->launches += 1;
-        h->pose_host_ok = rc == EKF_OK;
-        return rc;
+        h->pred_tw[0] = dtheta;
+        h->pred_tw[1] = dx;
+        h->pred_pending = true;
+        return EKF_OK;
     }
     if (h->pending > 0 && !h->carry_pending) {
         int rc = stream_flush(h, h->pending, nullptr);
@@ -659,7 +679,12 @@ int ekf_measurement(ekf_filter* h, const double* xy, const uint8_t* visible) {
         if (rc) return rc;
         memcpy(slot, xy, sizeof(double) * 2 * n);
         memcpy(slot + sizeof(double) * 2 * n, visible, n);
-        FusedParams p = fused_params(h, kDoMeasurement, 1);
+        double* tw = reinterpret_cast<double*>(slot + sizeof(double) * 2 * n + ((n + 7) & ~7));
+        tw[0] = h->pred_tw[0];
+        tw[1] = h->pred_tw[1];
+        FusedParams p = fused_params(h, kDoMeasurement | (h->pred_pending ? kDoPredict : 0), 1);
+        h->pred_pending = false;
+        p.twists = tw;
         p.xy = reinterpret_cast<const double*>(slot);
         p.vis = slot + sizeof(double) * 2 * n;
         rc = launch_fused(p, h->stream, h->device);
@@ -696,7 +721,7 @@ int ekf_data_association(ekf_filter* h, const double* xy, int m, uint8_t* known,
                          double* dmin_out, double* second_out, uint8_t* created_out) {
     if (!h || !known || m < 0 || (m > 0 && !xy)) return fail(EKF_ERR_INVALID, "invalid argument");
     DeviceGuard g(h->device);
-    {
+    if (h->engine != EKF_ENGINE_FUSED) {  // (the small engine's pending prediction rides along with the kernel below)
         int rc_ = stream_settle(h);
         if (rc_) return rc_;
     }
@@ -725,7 +750,12 @@ int ekf_data_association(ekf_filter* h, const double* xy, int m, uint8_t* known,
     int* o_kc = reinterpret_cast<int*>(o_known + ((n + 15) & ~15));
     if (h->engine == EKF_ENGINE_FUSED) {
         // the kernel reads the slot and writes the log straight into the pinned areas (device mapping of both)
-        FusedParams p = fused_params(h, kDoAssociation, m);
+        double* tw = reinterpret_cast<double*>(slot_i + 4);
+        tw[0] = h->pred_tw[0];
+        tw[1] = h->pred_tw[1];
+        FusedParams p = fused_params(h, kDoAssociation | (h->pred_pending ? kDoPredict : 0), m);
+        h->pred_pending = false;
+        p.twists = tw;
         p.xy = reinterpret_cast<const double*>(slot);
         p.known = slot + sizeof(double) * 2 * m;
         p.mcount = slot_i;
@@ -814,6 +844,10 @@ int ekf_maha(ekf_filter* h, double mx, double my, int landmark, double* d_out) {
 int ekf_get_state(ekf_filter* h, double* out) {
     if (!h || !out) return fail(EKF_ERR_INVALID, "null argument");
     DeviceGuard g(h->device);
+    {
+        int rc_ = settle_prediction(h);
+        if (rc_) return rc_;
+    }
     CU(cudaMemcpyAsync(out, h->d_state, sizeof(double) * h->N, cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     return EKF_OK;
@@ -821,6 +855,10 @@ int ekf_get_state(ekf_filter* h, double* out) {
 int ekf_set_state(ekf_filter* h, const double* in) {
     if (!h || !in) return fail(EKF_ERR_INVALID, "null argument");
     DeviceGuard g(h->device);
+    {
+        int rc_ = settle_prediction(h);
+        if (rc_) return rc_;
+    }
     h->pose_host_ok = false;
     CU(cudaMemcpyAsync(h->d_state, in, sizeof(double) * h->N, cudaMemcpyHostToDevice, h->stream));
     CU(cudaStreamSynchronize(h->stream));
@@ -829,6 +867,10 @@ int ekf_set_state(ekf_filter* h, const double* in) {
 int ekf_get_pose(ekf_filter* h, double* out3) {
     if (!h || !out3) return fail(EKF_ERR_INVALID, "null argument");
     DeviceGuard g(h->device);
+    {
+        int rc_ = settle_prediction(h);
+        if (rc_) return rc_;
+    }
     if (h->engine == EKF_ENGINE_FUSED && h->pose_host_ok && !h->external) {
         CU(cudaStreamSynchronize(h->stream));  // the last kernel left the pose in pinned memory
         out3[0] = h->h_pose[0];
@@ -843,6 +885,10 @@ int ekf_get_pose(ekf_filter* h, double* out3) {
 int ekf_get_landmarks(ekf_filter* h, double* out) {
     if (!h || !out) return fail(EKF_ERR_INVALID, "null argument");
     DeviceGuard g(h->device);
+    {
+        int rc_ = settle_prediction(h);
+        if (rc_) return rc_;
+    }
     CU(cudaMemcpyAsync(out, h->d_state + 3, sizeof(double) * 2 * h->n, cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     return EKF_OK;
@@ -903,6 +949,10 @@ int ekf_set_sigma(ekf_filter* h, const double* in, int64_t ld) {
 int ekf_get_init_flag(ekf_filter* h, int* out) {
     if (!h || !out) return fail(EKF_ERR_INVALID, "null argument");
     DeviceGuard g(h->device);
+    {
+        int rc_ = settle_prediction(h);
+        if (rc_) return rc_;
+    }
     int32_t v = 0;
     CU(cudaMemcpyAsync(&v, h->d_init_flag, sizeof(v), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
@@ -912,6 +962,10 @@ int ekf_get_init_flag(ekf_filter* h, int* out) {
 int ekf_set_init_flag(ekf_filter* h, int v) {
     if (!h) return fail(EKF_ERR_INVALID, "null handle");
     DeviceGuard g(h->device);
+    {
+        int rc_ = settle_prediction(h);
+        if (rc_) return rc_;
+    }
     const int32_t f = v ? 1 : 0;
     CU(cudaMemcpyAsync(h->d_init_flag, &f, sizeof(f), cudaMemcpyHostToDevice, h->stream));
     CU(cudaStreamSynchronize(h->stream));
@@ -992,6 +1046,10 @@ int ekf_launch_count(ekf_filter* h, uint64_t* out) {
 int ekf_timer_start(ekf_filter* h) {
     if (!h) return fail(EKF_ERR_INVALID, "null handle");
     DeviceGuard g(h->device);
+    {
+        int rc_ = settle_prediction(h);
+        if (rc_) return rc_;
+    }
     if (!h->t0) {
         CU(cudaEventCreate(&h->t0));
         CU(cudaEventCreate(&h->t1));

@@ -181,6 +181,46 @@ def test_pose_read_path_follows_every_way_the_state_can_change(gpu_pkg):
     assert (f.getStateTheta(), f.getStateX(), f.getStateY()) == (1.0, 2.0, 3.0)
 
 
+def test_deferred_prediction_is_invisible(gpu_pkg):
+    """On the small engine prediction() only records the twist; it is applied by the next measurement() /
+    data_association() kernel or by whatever verb looks at the filter first.  No call order may see the difference."""
+    tr = _trace(gpu_pkg, 20, 8, seed=12)
+    f = gpu_pkg.EKF_SLAM(20)
+    o = OracleEKF(20)
+    tw = [tuple(tr["twists"][t, 0]) for t in range(8)]
+    # two predictions in a row, then a getter
+    for t in (0, 1):
+        f.prediction(tw[t])
+        o.prediction(*tw[t])
+    assert state_err(f.state, o.state) < TOL
+    # prediction, then verbs that read Sigma / distances / copies
+    f.measurement(tr["xy"][2, 0], tr["vis"][2, 0])
+    o.measurement(tr["xy"][2, 0], tr["vis"][2, 0])
+    f.prediction(tw[3])
+    o.prediction(*tw[3])
+    assert abs(f.calculate_maha_dis((0.3, -0.2), 1) - o.maha(0.3, -0.2, 1)) <= 1e-9 * max(1.0, abs(o.maha(0.3, -0.2, 1)))
+    f.prediction(tw[4])
+    o.prediction(*tw[4])
+    g = f.clone()
+    assert sigma_err(g.sigma, o.sigma) < TOL and state_err(g.state, o.state) < TOL
+    assert np.array_equal(g.sigma, f.sigma) and np.array_equal(g.state, f.state)
+    # prediction, an EMPTY association call (nothing to launch), then the measurement that carries it
+    known = np.ones(20, np.uint8)
+    f.prediction(tw[5])
+    o.prediction(*tw[5])
+    f.data_association(np.zeros((0, 2)), known)
+    f.measurement(tr["xy"][6, 0], tr["vis"][6, 0])
+    o.measurement(tr["xy"][6, 0], tr["vis"][6, 0])
+    assert sigma_err(f.sigma, o.sigma) < TOL and state_err(f.state, o.state) < TOL
+    # prediction, then a state overwrite: the prediction comes first, the overwrite wins
+    f.prediction(tw[7])
+    o.prediction(*tw[7])
+    s0 = o.state.copy()
+    s0[:3] = [0.1, 0.2, 0.3]
+    f.state = s0
+    assert np.array_equal(f.state, s0) and sigma_err(f.sigma, o.sigma) < TOL
+
+
 def test_normalize_angle_device_twin_is_bit_exact(gpu_pkg):
     """rigid2d::normalize_angle: the device twin must equal the C library fmod formulation bit for bit."""
     import ctypes
