@@ -57,7 +57,10 @@ int ekf_num_landmarks(const ekf_filter* h);
 int ekf_engine(const ekf_filter* h);
 
 /* EKF_SLAM::prediction(const Twist2D&): dtheta = twist.angular(), dx = twist.linearX();
- * linearY is ignored by the reference (:70)                     rigid2d/src/ekf_slam.cpp:55-106 */
+ * linearY is ignored by the reference (:70)                     rigid2d/src/ekf_slam.cpp:55-106
+ * Fused engine: the call records the twist and returns; the prediction is applied by the next ekf_measurement() /
+ * ekf_data_association() kernel, or by whichever other verb looks at or changes the filter first (results are the
+ * same for every call order; a launch error of the deferred work is returned by that later verb). */
 int ekf_predict(ekf_filter* h, double dtheta, double dx);
 
 /* EKF_SLAM::measurement(mat sensor_reading, vector<bool> visible_list, vector<bool> known_list)
