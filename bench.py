@@ -206,12 +206,14 @@ def parity_cfg3(bt, tr, n, picks=64, seed=5):
             "tol": PARITY_TOL, "checker": "oracle/ekf_oracle.c (plain-C restatement pinned to the reference build)"}
 
 
-def parity_large_map(pkg, device, n_lm, tr, min_corrections=10):
+def parity_large_map(pkg, device, n_lm, tr, min_corrections=10, max_pending=None):
     """cfg4 size: a fresh streamed filter and the O(N^2) oracle through the init-only call and as many steps as it
     takes to pile up >= min_corrections corrections (they stay pending on the GPU and go through ONE multi-factor
     sweep when Sigma is read); state and the FULL covariance compared.  Also times the oracle (CPU baseline)."""
     import _oracle
     f = pkg.EKF_SLAM(n_lm, device=device)
+    if max_pending:
+        f.set_max_pending(max_pending)
     o = _oracle.OracleEKF(n_lm)
     N = 3 + 2 * n_lm
     done, t, cpu_s, cpu_n = 0, 0, 0.0, 0
@@ -327,30 +329,36 @@ def large_map_leg(pkg, device, n_lm, timed_updates, peak_gbs, want_cpu):
     w = tg.grid_world(nx, ny, pitch=0.5, n_slots=n_lm, max_visible=0.7)
     steps = 64
     tr = tg.simulate_known(w, 1, steps, seed=99)
-    f = pkg.EKF_SLAM(n_lm, device=device)
-    if os.environ.get("EKF_BENCH_MAX_PENDING"):  # tuning aid
-        f.set_max_pending(int(os.environ["EKF_BENCH_MAX_PENDING"]))
     N = 3 + 2 * n_lm
-    # first call: initialise every landmark (ekf_slam.cpp:113-128), then a few warm-up steps, then ONE timed region
-    # over whole SLAM steps until `timed_updates` corrections are done.  Factors stay pending across steps, so the
-    # region ends with the flush that timer_stop() triggers (inside the timed region).
-    t = 0
-    while t < 3:
-        f.prediction(tuple(tr["twists"][t, 0]))
-        f.measurement(tr["xy"][t, 0], tr["vis"][t, 0])
-        t += 1
-    f.sync()
-    l0, s0 = f.launch_count, f.sweep_count
-    done = 0
-    f.timer_start()
-    while t < steps and done < timed_updates:
-        f.prediction(tuple(tr["twists"][t, 0]))
-        f.measurement(tr["xy"][t, 0], tr["vis"][t, 0])
-        done += int(tr["vis"][t, 0].sum())
-        t += 1
-    sweep_ms_total = f.timer_stop()
-    launches = f.launch_count - l0
-    n_sweeps = f.sweep_count - s0
+
+    def timed(max_pending):
+        # first call: initialise every landmark (ekf_slam.cpp:113-128), then a few warm-up steps, then ONE timed region
+        # over whole SLAM steps until `timed_updates` corrections are done.  Factors stay pending across steps, so the
+        # region ends with the flush that timer_stop() triggers (inside the timed region).
+        f = pkg.EKF_SLAM(n_lm, device=device)
+        if max_pending:
+            f.set_max_pending(max_pending)
+        t = 0
+        while t < 3:
+            f.prediction(tuple(tr["twists"][t, 0]))
+            f.measurement(tr["xy"][t, 0], tr["vis"][t, 0])
+            t += 1
+        f.sync()
+        l0, s0 = f.launch_count, f.sweep_count
+        done = 0
+        f.timer_start()
+        while t < steps and done < timed_updates:
+            f.prediction(tuple(tr["twists"][t, 0]))
+            f.measurement(tr["xy"][t, 0], tr["vis"][t, 0])
+            done += int(tr["vis"][t, 0].sum())
+            t += 1
+        ms = f.timer_stop()
+        res = (ms, done, f.launch_count - l0, f.sweep_count - s0)
+        f.close()
+        return res
+
+    env_p = int(os.environ["EKF_BENCH_MAX_PENDING"]) if os.environ.get("EKF_BENCH_MAX_PENDING") else None  # tuning aid
+    sweep_ms_total, done, launches, n_sweeps = timed(env_p)
     ms_upd = sweep_ms_total / max(done, 1)
     alg_bytes = 16.0 * N * N
     out = {
@@ -370,10 +378,21 @@ def large_map_leg(pkg, device, n_lm, timed_updates, peak_gbs, want_cpu):
                      "note": "one launch moves Sigma once (16 N^2 B) and applies up to 14 pending corrections; per_update_* "
                              "is SURVEY.md's 16 N^2-per-correction convention and exceeds 1 for that reason"},
     }
-    f.close()
     # untimed: parity at this size through the multi-factor sweep, against the O(N^2) oracle (which is the CPU baseline)
     par, cpu = parity_large_map(pkg, device, n_lm, tr)
     out["parity"] = par
+    # the same leg with 20 corrections per sweep (ekf_set_max_pending): fewer passes over Sigma per correction, more
+    # corrections/s, but the sweep is then bound by the FP64 pipe and no longer a copy - reported beside the default
+    ms20, done20, launches20, sweeps20 = timed(20)
+    par20, _ = parity_large_map(pkg, device, n_lm, tr, min_corrections=22, max_pending=20)
+    out["deep_pending"] = {
+        "max_pending": 20, "value": 1e3 * done20 / ms20, "unit": UNIT, "updates_timed": done20, "ms_per_update": ms20 / max(done20, 1),
+        "gpu_launches": int(launches20), "sweeps": int(sweeps20), "updates_per_sweep": done20 / max(sweeps20, 1),
+        "roofline": {"bound": "fp64 pipe (DMMA): 2 x 20 FMAs per element next to the copy", "unit": "GB/s", "peak": peak_gbs,
+                     "achieved": alg_bytes * sweeps20 / (ms20 * 1e-3) / 1e9,
+                     "frac": alg_bytes * sweeps20 / (ms20 * 1e-3) / 1e9 / peak_gbs,
+                     "kernel": "k_large_sweep_mma_t<P, 256, 16, 4> (narrow tiles: the W fragments of 20 factors fit the registers)"},
+        "parity": par20}
     if want_cpu:
         out["cpu_baseline"] = cpu
         dense = cpu_reference_dense_scaling(pkg)
@@ -965,6 +984,8 @@ def run_ours(args):
     parity = {"cfg3": par3}
     if "large_map" in line:
         parity["cfg4"] = line["large_map"]["parity"]
+        if "deep_pending" in line["large_map"]:
+            parity["cfg4_20_per_sweep"] = line["large_map"]["deep_pending"]["parity"]
     if "sharded_map" in line:
         parity["cfg5"] = line["sharded_map"]["parity"]
         parity["nccl_ranks"] = world

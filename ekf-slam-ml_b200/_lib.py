@@ -144,6 +144,7 @@ SIGNATURES_SHARDED = {
     "ekf_sharded_data_association": (ctypes.c_int, [ctypes.c_void_p, c_double_p, ctypes.c_int, c_u8_p, c_i32_p,
                                                     c_double_p, c_double_p, c_u8_p]),
     "ekf_sharded_get_state": (ctypes.c_int, [ctypes.c_void_p, c_double_p]),
+    "ekf_sharded_set_max_pending": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     "ekf_sharded_exchange_bytes": (ctypes.c_int, [ctypes.c_void_p, c_u64_p]),
     "ekf_sharded_attach_exchange": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, c_u64_p, ctypes.c_uint64]),
     "ekf_sharded_rows": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, c_i64_p, c_i64_p]),

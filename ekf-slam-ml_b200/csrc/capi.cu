@@ -296,7 +296,7 @@ struct ekf_filter {
     double2* d_W2 = nullptr;  // [kMaxPending][ld] pending H*Sigma factors
     double* d_state_alt = nullptr;  // ping-pong partner of d_state (the gain kernel never writes what it reads)
     int pending = 0;                // corrections computed but not yet applied to Sigma
-    int max_pending = kMaxPending;  // flush threshold (1 = the reference's one sweep per correction)
+    int max_pending = kDefaultPending;  // flush threshold (1 = the reference's one sweep per correction)
     int carry_pending = 1;          // factors may stay pending across prediction() / measurement() calls
     uint64_t sweeps = 0;            // passes over Sigma so far (streamed engine)
     double* d_motion = nullptr;
@@ -1008,7 +1008,7 @@ int ekf_device_pointers(ekf_filter* h, void** sigma, int64_t* ld, void** state) 
     h->external = true;
     return EKF_OK;
 }
-// How many corrections the streamed engine may accumulate before it sweeps Sigma (1..kMaxPending = 14, default 14).  The result
+// How many corrections the streamed engine may accumulate before it sweeps Sigma (1..kMaxPending = 20, default 14).  The result
 // is bit-identical for every setting; 1 reproduces the reference's schedule of one full pass per correction.
 int ekf_set_max_pending(ekf_filter* h, int max_pending) {
     if (!h || max_pending < 1 || max_pending > kMaxPending) return fail(EKF_ERR_INVALID, "max_pending must be 1..%d", kMaxPending);

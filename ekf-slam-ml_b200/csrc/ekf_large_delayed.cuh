@@ -11,12 +11,16 @@
 
 namespace ekf {
 
-// 14: measured optimum of the TMA sweep on B200 at N = 16,387 (per correction, whole period: 0.101 ms at 8, 0.086 at 10,
-// 0.078 at 12, 0.073 at 14, 0.093 at 16: 2 x 16 FMAs per element no longer hide behind the copy)
+// Capacity (factor slots) and default depth of the delayed application.  Up to 14 pending corrections the sweep is
+// still a copy (0.90 of the measured HBM peak at N = 16,387: the DMMA time hides behind it) - that is the default.
+// Deeper groups (15..20, ekf_set_max_pending) go through the narrow-tile sweep of ekf_large_mma.cuh: fewer passes over
+// Sigma per correction and more corrections/s (cfg4: 18.6k against 16.5k at 20), but the sweep is then bound by the
+// FP64 pipe, not by HBM (0.66 of the copy peak per sweep period).
 #ifndef EKF_MAX_PENDING
-#define EKF_MAX_PENDING 14
+#define EKF_MAX_PENDING 20
 #endif
 constexpr int kMaxPending = EKF_MAX_PENDING;
+constexpr int kDefaultPending = kMaxPending < 14 ? kMaxPending : 14;
 
 struct GainSharedP {
     Hj h;

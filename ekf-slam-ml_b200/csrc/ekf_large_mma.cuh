@@ -172,6 +172,171 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
     if (warp == kTmaConsumerWarps + 1 && lane == 0) bulk_wait_all();  // drain before the CTA's shared memory goes away
 }
 
+// ---- more than 14 corrections per pass ------------------------------------------------------------------------
+// Above P = 14 the W fragments of a 64-column consumer warp (8 blocks x ceil(P/2) doubles) no longer fit the register
+// file.  This variant cuts the tile to 256 columns (32 per consumer warp: 4 x ceil(P/2) fragment doubles) and makes
+// a stage 16 rows instead of 8, so a stage is still 33 KB and one mbarrier round trip buys the same amount of work.
+template <int P, int COLS, int SROWS, int STAGES>
+struct MmaT {
+    static constexpr int KS = (2 * P + 3) / 4;
+    static constexpr int NBW = COLS / (8 * kTmaConsumerWarps);
+    static constexpr int RG = SROWS / 8;
+    static constexpr int RS = COLS + 8;  // row stride in doubles: 64 B past a multiple of 128 B
+    static constexpr int kTileBytes = SROWS * RS * 8;
+    static constexpr int kKBytes = P * SROWS * 16;
+    static constexpr int kSmemBytes = STAGES * (kTileBytes + kKBytes) + 3 * STAGES * 8 + 64;
+};
+
+template <int P, int COLS, int SROWS, int STAGES>
+__global__ void __launch_bounds__(kTmaThreads, 1)
+    k_large_sweep_mma_t(double* __restrict__ sig, long long ld, int n_rows, const double2* __restrict__ Kp,
+                        const double2* __restrict__ Wp, long long row0, unsigned long long* __restrict__ n_updates,
+                        int n_counted, const UpdateCmd* __restrict__ cmd) {
+    using T = MmaT<P, COLS, SROWS, STAGES>;
+    constexpr int KS = T::KS, NBW = T::NBW, RG = T::RG, RS = T::RS;
+    pdl_prologue();
+    if (cmd && !cmd->do_update) return;
+    if (blockIdx.x == 0 && threadIdx.x == 0 && n_updates) *n_updates += (unsigned long long)n_counted;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double* tiles = reinterpret_cast<double*>(smem_raw);                                   // [STAGES][SROWS][RS]
+    double2* ksm = reinterpret_cast<double2*>(smem_raw + (size_t)STAGES * T::kTileBytes);  // [STAGES][P][SROWS]
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)STAGES * (T::kTileBytes + T::kKBytes));
+    uint64_t* done = full + STAGES;
+    uint64_t* empty = done + STAGES;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(full + s, 1);
+            mbar_init(done + s, kTmaConsumerWarps);
+            mbar_init(empty + s, 1);
+        }
+        fence_mbar_init();
+    }
+    __syncthreads();
+
+    const int chunks = (int)((ld + COLS - 1) / COLS);
+    const int row_units = (n_rows + kUnitRows - 1) / kUnitRows;
+    const long long units = (long long)chunks * row_units;
+    int stage = 0;
+    uint32_t phase = 0;
+    bool first = true;
+
+    for (long long u = blockIdx.x; u < units; u += gridDim.x) {
+        const int cu = (int)(u % chunks), ru = (int)(u / chunks);
+        const long long c0 = (long long)cu * COLS;
+        const int width = (int)(ld - c0 < COLS ? ld - c0 : COLS);  // multiple of 16 doubles
+        const int r_begin = ru * kUnitRows;
+        const int r_end = r_begin + kUnitRows < n_rows ? r_begin + kUnitRows : n_rows;
+        const int groups = (r_end - r_begin + SROWS - 1) / SROWS;
+        if (warp == 0) {
+            // ---------------------------------------------------------------- producer
+            if (lane == 0) {
+                for (int g = 0; g < groups; ++g) {
+                    mbar_wait(empty + stage, phase ^ 1u);
+                    const int r = r_begin + g * SROWS;
+                    const int nr = r_end - r < SROWS ? r_end - r : SROWS;
+                    mbar_arrive_expect_tx(full + stage, (uint32_t)(nr * width * 8 + P * SROWS * 16));
+                    double* tile = tiles + (size_t)stage * SROWS * RS;
+                    for (int k = 0; k < nr; ++k)
+                        bulk_g2s(tile + k * RS, sig + (long long)(r + k) * ld + c0, (uint32_t)(width * 8), full + stage);
+                    for (int j = 0; j < P; ++j)
+                        bulk_g2s(ksm + ((size_t)stage * P + j) * SROWS, Kp + (long long)j * ld + row0 + r, SROWS * 16, full + stage);
+                    if (++stage == STAGES) {
+                        stage = 0;
+                        phase ^= 1u;
+                    }
+                }
+            }
+        } else if (warp <= kTmaConsumerWarps) {
+            // ---------------------------------------------------------------- consumers
+            const int w = warp - 1;
+            const int g = lane >> 2, t = lane & 3;
+            const int wc0 = 8 * NBW * w;  // this warp's first column inside the tile
+            double bf[NBW][KS];           // B[k][n] of k-step s and block b, as in k_large_sweep_mma
+#pragma unroll
+            for (int b = 0; b < NBW; ++b) {
+                const int c = wc0 + 8 * b + g;
+#pragma unroll
+                for (int s = 0; s < KS; ++s) {
+                    const int kk = 4 * s + t, j = kk >> 1;
+                    bf[b][s] = (j < P && c < width)
+                                   ? reinterpret_cast<const double*>(Wp + (long long)j * ld + c0 + c)[kk & 1]
+                                   : 0.0;
+                }
+            }
+            const int nblk = width - wc0 >= 8 * NBW ? NBW : (width - wc0 > 0 ? (width - wc0) / 8 : 0);  // warp-uniform
+            for (int gi = 0; gi < groups; ++gi) {
+                mbar_wait(full + stage, phase);
+                double* tile = tiles + (size_t)stage * SROWS * RS;
+                const double* kst = reinterpret_cast<const double*>(ksm + (size_t)stage * P * SROWS);
+#pragma unroll
+                for (int rg = 0; rg < RG; ++rg) {
+                    double af[KS];  // A[g][k] = -K_j[row 8 rg + g of the stage].{x | y}
+#pragma unroll
+                    for (int s = 0; s < KS; ++s) {
+                        const int kk = 4 * s + t, j = kk >> 1;
+                        af[s] = j < P ? -kst[2 * (j * SROWS + 8 * rg + g) + (kk & 1)] : 0.0;
+                    }
+                    double* cp = tile + (8 * rg + g) * RS + wc0 + 2 * t;
+                    double2 cf[NBW];
+#pragma unroll
+                    for (int b = 0; b < NBW; ++b)
+                        if (b < nblk) cf[b] = *reinterpret_cast<const double2*>(cp + 8 * b);
+#pragma unroll
+                    for (int s = 0; s < KS; ++s)
+#pragma unroll
+                        for (int b = 0; b < NBW; ++b)
+                            if (b < nblk)
+                                asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                                             : "+d"(cf[b].x), "+d"(cf[b].y)
+                                             : "d"(af[s]), "d"(bf[b][s]));
+#pragma unroll
+                    for (int b = 0; b < NBW; ++b)
+                        if (b < nblk) *reinterpret_cast<double2*>(cp + 8 * b) = cf[b];
+                }
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(done + stage);
+                if (++stage == STAGES) {
+                    stage = 0;
+                    phase ^= 1u;
+                }
+            }
+        } else {
+            // ---------------------------------------------------------------- store warp
+            if (lane == 0) {
+                for (int g = 0; g < groups; ++g) {
+                    const int r = r_begin + g * SROWS;
+                    const int nr = r_end - r < SROWS ? r_end - r : SROWS;
+                    mbar_wait(done + stage, phase);
+                    double* tile = tiles + (size_t)stage * SROWS * RS;
+                    for (int k = 0; k < nr; ++k)
+                        bulk_s2g(sig + (long long)(r + k) * ld + c0, tile + k * RS, (uint32_t)(width * 8));
+                    bulk_commit();
+                    bulk_wait_read_1();  // every store but the newest has finished reading shared memory
+                    if (!first) mbar_arrive(empty + (stage == 0 ? STAGES - 1 : stage - 1));
+                    first = false;
+                    if (++stage == STAGES) {
+                        stage = 0;
+                        phase ^= 1u;
+                    }
+                }
+            }
+        }
+    }
+    if (warp == kTmaConsumerWarps + 1 && lane == 0) bulk_wait_all();  // drain before the CTA's shared memory goes away
+}
+
+#ifndef EKF_MMA_T_COLS
+#define EKF_MMA_T_COLS 256
+#endif
+#ifndef EKF_MMA_T_SROWS
+#define EKF_MMA_T_SROWS 16
+#endif
+#ifndef EKF_MMA_T_STAGES
+#define EKF_MMA_T_STAGES 4
+#endif
+
 // Dispatch: register path for 1-2 factors, DMMA pipeline from 3 on.  Kp must have at least kStageRows pairs of slack
 // after its last used row (the stage's K rows are fetched 8 at a time).
 inline cudaError_t launch_sweep_mma(int pending, double* sig, long long ld, int n_rows, const double2* Kp,
@@ -195,6 +360,21 @@ inline cudaError_t launch_sweep_mma(int pending, double* sig, long long ld, int 
                                                                              n_counted, cmd);                        \
         break;                                                                                                        \
     }
+#define EKF_MMA_T_CASE(PP)                                                                                            \
+    case PP: {                                                                                                        \
+        using TT = MmaT<PP, EKF_MMA_T_COLS, EKF_MMA_T_SROWS, EKF_MMA_T_STAGES>;                                       \
+        auto kern = k_large_sweep_mma_t<PP, EKF_MMA_T_COLS, EKF_MMA_T_SROWS, EKF_MMA_T_STAGES>;                       \
+        static bool attr_set[64] = {false};                                                                           \
+        if (dev < 0 || dev >= 64 || !attr_set[dev]) {                                                                 \
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TT::kSmemBytes);  \
+            if (e != cudaSuccess) return e;                                                                           \
+            if (dev >= 0 && dev < 64) attr_set[dev] = true;                                                           \
+        }                                                                                                             \
+        const long long units_t = ((ld + EKF_MMA_T_COLS - 1) / EKF_MMA_T_COLS) * ((n_rows + kUnitRows - 1) / kUnitRows); \
+        const unsigned grid_t = (unsigned)(units_t < sm_count ? (units_t < 1 ? 1 : units_t) : sm_count);             \
+        kern<<<grid_t, kTmaThreads, TT::kSmemBytes, stream>>>(sig, ld, n_rows, Kp, Wp, row0, n_updates, n_counted, cmd); \
+        break;                                                                                                        \
+    }
     switch (pending) {
         EKF_MMA_CASE(3)
         EKF_MMA_CASE(4)
@@ -209,19 +389,20 @@ inline cudaError_t launch_sweep_mma(int pending, double* sig, long long ld, int 
         EKF_MMA_CASE(13)
         EKF_MMA_CASE(14)
 #if EKF_MAX_PENDING > 14
-        EKF_MMA_CASE(15)
-        EKF_MMA_CASE(16)
+        EKF_MMA_T_CASE(15)
+        EKF_MMA_T_CASE(16)
 #endif
 #if EKF_MAX_PENDING > 16
-        EKF_MMA_CASE(17)
-        EKF_MMA_CASE(18)
-        EKF_MMA_CASE(19)
-        EKF_MMA_CASE(20)
+        EKF_MMA_T_CASE(17)
+        EKF_MMA_T_CASE(18)
+        EKF_MMA_T_CASE(19)
+        EKF_MMA_T_CASE(20)
 #endif
         default:
             return cudaErrorInvalidValue;
     }
 #undef EKF_MMA_CASE
+#undef EKF_MMA_T_CASE
     return cudaGetLastError();
 }
 

@@ -761,6 +761,7 @@ struct ekf_sharded {
     int init_flag_host = 0;
     int pending = 0;  // corrections whose factors are not yet applied to Sigma
     int carry_pending = 1;  // factors may stay pending across prediction() / measurement() calls
+    int max_pending = kDefaultPending;  // corrections per sweep (ekf_sharded_set_max_pending)
     uint64_t sweeps = 0;    // passes over Sigma so far
     int m_cap = 0;
     const double2** d_srcs = nullptr;  // local mode: device array of Wpart pointers
@@ -977,7 +978,7 @@ int correct(ekf_sharded* h, bool use_cmd, bool stale_pose, int lm, double sx, do
                       h->corrections_enqueued * (unsigned long long)gl));
         h->launches += 1;
         h->pending += 1;
-        if (!use_cmd && h->pending == kMaxPending) return flush(h, kMaxPending, false);
+        if (!use_cmd && h->pending >= h->max_pending) return flush(h, h->pending, false);
         return 0;
     }
     if (h->push) {
@@ -990,7 +991,7 @@ int correct(ekf_sharded* h, bool use_cmd, bool stale_pose, int lm, double sx, do
                       s.W2 + (long long)p * h->ld, s.K2 + (long long)p * h->ld, s.state, (const Ctx*)s.ctx, h->N, h->ld));
         h->launches += 2;
         h->pending += 1;
-        if (!use_cmd && h->pending == kMaxPending) return flush(h, kMaxPending, false);
+        if (!use_cmd && h->pending >= h->max_pending) return flush(h, h->pending, false);
         return 0;
     }
     for (auto& s : h->sh) {
@@ -1009,7 +1010,7 @@ int correct(ekf_sharded* h, bool use_cmd, bool stale_pose, int lm, double sx, do
     CU(cudaGetLastError());
     h->pending += 1;
     // a correction data_association() may still drop (use_cmd) is flushed by the caller with the command block
-    if (!use_cmd && h->pending == kMaxPending) return flush(h, kMaxPending, false);
+    if (!use_cmd && h->pending >= h->max_pending) return flush(h, h->pending, false);
     return 0;
 }
 
@@ -1394,6 +1395,12 @@ int ekf_sharded_update_count(ekf_sharded* h, uint64_t* out) {
     CU(cudaStreamSynchronize(h->stream));
     *out = v;
     return 0;
+}
+int ekf_sharded_set_max_pending(ekf_sharded* h, int max_pending) {
+    if (!h || max_pending < 1 || max_pending > kMaxPending) return fail(-1, "max_pending must be 1..%d", kMaxPending);
+    Dev g(h->device);
+    h->max_pending = max_pending;
+    return h->pending >= max_pending ? settle(h) : 0;
 }
 int ekf_sharded_sweep_count(ekf_sharded* h, uint64_t* out) {
     if (!h || !out) return fail(-1, "null argument");

@@ -263,7 +263,7 @@ class EKF_SLAM:
         return v.value
 
     def set_max_pending(self, k):
-        """Streamed engine: corrections accumulated per pass over Sigma (1..14); results do not depend on it."""
+        """Streamed engine: corrections accumulated per pass over Sigma (1..20, default 14); results do not depend on it."""
         check(self._L.ekf_set_max_pending(self._h, int(k)))
 
     def set_carry_pending(self, on):

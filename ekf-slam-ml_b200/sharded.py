@@ -162,6 +162,10 @@ class ShardedEKF:
         """Let correction factors stay pending across prediction() / measurement() calls (default on)."""
         _check(self._L.ekf_sharded_set_carry_pending(self._h, 1 if on else 0))
 
+    def set_max_pending(self, k):
+        """Corrections per sweep, 1..20 (default 14); every rank must use the same value."""
+        _check(self._L.ekf_sharded_set_max_pending(self._h, int(k)))
+
     def sync(self):
         _check(self._L.ekf_sharded_sync(self._h))
 

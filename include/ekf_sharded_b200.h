@@ -58,6 +58,8 @@ int ekf_sharded_update_count(ekf_sharded* h, uint64_t* out);
 /* As ekf_set_carry_pending / ekf_sweep_count of ekf_slam_b200.h: correction factors stay pending across prediction()
  * and measurement() calls by default (every rank must use the same setting); verbs that read Sigma settle them. */
 int ekf_sharded_set_carry_pending(ekf_sharded* h, int carry);
+/* As ekf_set_max_pending (1..20, default 14); collective: every rank must use the same setting */
+int ekf_sharded_set_max_pending(ekf_sharded* h, int max_pending);
 int ekf_sharded_sweep_count(ekf_sharded* h, uint64_t* out);
 int ekf_sharded_launch_count(ekf_sharded* h, uint64_t* out);
 int ekf_sharded_sync(ekf_sharded* h);

@@ -102,9 +102,10 @@ int ekf_get_init_flag(ekf_filter* h, int* out);  /* landmark_init_flag, ekf_slam
 int ekf_set_init_flag(ekf_filter* h, int v);
 int ekf_update_count(ekf_filter* h, uint64_t* out); /* landmark corrections executed so far */
 int ekf_sync(ekf_filter* h);
-/* Streamed engine only: corrections accumulated before Sigma is swept (1..14, default 14: the measured optimum of
- * the sweep kernel).  Within a measurement() call the delayed application is bit-identical to one sweep per correction
- * (1 reproduces the reference's schedule); across calls see ekf_set_carry_pending. */
+/* Streamed engine only: corrections accumulated before Sigma is swept (1..20, default 14: the deepest group for
+ * which the sweep still runs at the HBM copy rate; 15..20 give more corrections per second with a sweep bound by the
+ * FP64 pipe instead).  Within a measurement() call the delayed application is bit-identical to one sweep per
+ * correction (1 reproduces the reference's schedule); across calls see ekf_set_carry_pending. */
 int ekf_set_max_pending(ekf_filter* h, int max_pending);
 /* 1 (default): correction factors may stay pending across prediction() and measurement() calls (prediction() maps
  * them through the motion Jacobian in O(1)), so every sweep of the streamed engine carries max_pending corrections;

@@ -654,7 +654,7 @@ def test_delayed_application_is_bit_identical(gpu_pkg):
     w = tg.grid_world(20, 15, pitch=0.4, n_slots=n, max_visible=1.2)
     tr = tg.simulate_known(w, 1, 8, seed=21)
     outs = []
-    for k in (1, 3, 8):
+    for k in (1, 3, 8, 14, 20):  # 3..14: DMMA sweep on 512-column tiles, 15..20: the narrow-tile variant
         f = gpu_pkg.EKF_SLAM(n, engine=gpu_pkg.ENGINE_STREAM)
         f.set_max_pending(k)
         f.set_carry_pending(False)  # groups end with the measurement() call
@@ -662,11 +662,11 @@ def test_delayed_application_is_bit_identical(gpu_pkg):
             f.prediction(tuple(tr["twists"][t, 0]))
             f.measurement(tr["xy"][t, 0], tr["vis"][t, 0])
         outs.append((f.state, f.sigma, f.launch_count))
-    assert int(tr["vis"][1:].sum(axis=2).max()) > 8  # some steps need more than one group even at k = 8
+    assert int(tr["vis"][1:].sum(axis=2).max()) > 15  # some steps need more than one group at k = 8 and fill a group of 15+
     for st, sg, _ in outs[1:]:
         assert np.array_equal(st.view(np.uint64), outs[0][0].view(np.uint64))
         assert np.array_equal(sg.view(np.uint64), outs[0][1].view(np.uint64))
-    assert outs[2][2] < outs[0][2]  # fewer launches: fewer sweeps
+    assert outs[4][2] < outs[2][2] < outs[0][2]  # fewer launches: fewer sweeps
 
 
 def test_pending_factors_carried_across_prediction(gpu_pkg):
