@@ -419,6 +419,8 @@ def sharded_map_leg(pkg, dist, local, n_lm, timed_updates, peak_gbs):
     par_full = parity_sharded(pkg, dist, local, n_lm, tr, sample_rows=1000)
     dist.barrier()
     f = ShardedEKF.from_process_group(n_lm, dist, local)
+    if os.environ.get("EKF_BENCH_MAX_PENDING"):  # tuning aid: corrections per sweep (default 14)
+        f.set_max_pending(int(os.environ["EKF_BENCH_MAX_PENDING"]))
     N = 3 + 2 * n_lm
     t = 0
     while t < 2:  # init-only call + one warm-up step
