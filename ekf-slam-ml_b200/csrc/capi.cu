@@ -1012,6 +1012,9 @@ int ekf_device_pointers(ekf_filter* h, void** sigma, int64_t* ld, void** state) 
 // is bit-identical for every setting; 1 reproduces the reference's schedule of one full pass per correction.
 int ekf_set_max_pending(ekf_filter* h, int max_pending) {
     if (!h || max_pending < 1 || max_pending > kMaxPending) return fail(EKF_ERR_INVALID, "max_pending must be 1..%d", kMaxPending);
+#ifdef EKF_SWEEP_VECTOR  // the vector sweeps (ekf_large_tma.cuh) are instantiated up to 16 factors
+    if (max_pending > 16) return fail(EKF_ERR_UNSUPPORTED, "this build's vector sweep takes at most 16 corrections per pass");
+#endif
     h->max_pending = max_pending;
     if (h->pending >= max_pending) {
         DeviceGuard g(h->device);
