@@ -402,8 +402,9 @@ def large_map_leg(pkg, device, n_lm, timed_updates, peak_gbs, want_cpu):
 
 
 def sharded_map_leg(pkg, dist, local, n_lm, timed_updates, peak_gbs):
-    """cfg5: one filter, n_lm landmarks, Sigma row-block-sharded over all ranks (one NCCL all-reduce of W per
-    correction; K is formed locally on every rank).  Timed on the device, max over ranks."""
+    """cfg5: one filter, n_lm landmarks, Sigma row-block-sharded over all ranks (per correction the two owning ranks
+    store their partial W into every rank's exchange buffer from inside the correction kernel - or an NCCL all-reduce
+    with EKF_SHARDED_EXCHANGE=nccl; K is formed locally on every rank).  Timed on the device, max over ranks."""
     from ekf_slam_ml_b200.sharded import ShardedEKF
     tg = pkg.tracegen
     world = dist.get_world_size()
